@@ -1,0 +1,142 @@
+// bd_gemm.cu — C-ABI for the weight-streaming tcgen05 GEMM (kernel in bd_gemm.cuh).
+#include "bd_gemm.cuh"
+#include "bd_host.h"
+
+namespace bd {
+
+struct GemmPlan {
+  int bn;
+  int splits;
+};
+
+static GemmPlan plan_gemm(int M, int N, int K, int bn, int splits) {
+  const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+  const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+  const int sms = num_sms();
+  if (bn == 0) {
+    if (N <= 64)
+      bn = 64;
+    else
+      bn = (m_tiles * ((N + 127) / 128) > sms) ? 256 : 128;
+  }
+  const int tiles = m_tiles * ((N + bn - 1) / bn);
+  if (splits == 0) {
+    splits = sms / tiles;
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (splits > 8) splits = 8;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > num_kb) splits = num_kb;
+  return {bn, splits};
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, int splits, float* partial,
+                       const GemmEpi& epi, bool pdl, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BD_CUDA_TRY(cudaFuncSetAttribute(bd_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + BN - 1) / BN, splits);
+  LaunchCfg lc(grid, dim3(kGemmThreads), Cfg::kSmemBytes, stream, pdl);
+  // Re-reading A across N tiles should hit L2: ask TMA to keep it when it is small next to W.
+  const int a_hint_last = (static_cast<long long>(M) * K * 2 <= (32ll << 20)) ? 1 : 0;
+  BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, bd_gemm_kernel<BN>, ta, tw, M, N, K, splits, partial, epi, a_hint_last));
+  return BD_OK;
+}
+
+__global__ void bd_interleave16_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up,
+                                       __nv_bfloat16* __restrict__ out, int F, int K,
+                                       const __nv_bfloat16* __restrict__ bg, const __nv_bfloat16* __restrict__ bu,
+                                       __nv_bfloat16* __restrict__ bo) {
+  const int r = blockIdx.x;  // output row in [0, 2F)
+  const int blk = r >> 5, w = r & 31;
+  const int src = blk * 16 + (w & 15);
+  const __nv_bfloat16* s = (w < 16 ? gate : up) + static_cast<long long>(src) * K;
+  __nv_bfloat16* d = out + static_cast<long long>(r) * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) d[k] = s[k];
+  if (threadIdx.x == 0 && bo) bo[r] = (w < 16 ? bg : bu)[src];
+}
+
+}  // namespace bd
+
+using namespace bd;
+
+extern "C" {
+
+size_t bd_gemm_workspace_bytes(int M, int N, int K, int bn, int splits) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  GemmPlan p = plan_gemm(M, N, K, bn, splits);
+  return p.splits > 1 ? static_cast<size_t>(p.splits) * M * N * sizeof(float) : 0;
+}
+
+int bd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                 const bd_gemm_epilogue_t* e, void* workspace, size_t workspace_bytes, int bn, int splits, int flags,
+                 bd_stream_t stream_) {
+  BD_REQUIRE(A && W && e && e->out);
+  BD_REQUIRE(M > 0 && N > 0 && K > 0);
+  BD_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 256);
+  BD_REQUIRE(splits >= 0);
+  BD_REQUIRE(lda >= K && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0);
+  BD_REQUIRE(!e->swiglu || ((N % 32) == 0 && !e->gate && !e->res && !e->out_f32 && e->act == 0));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GemmPlan p = plan_gemm(M, N, K, bn, splits);
+  float* partial = nullptr;
+  if (p.splits > 1) {
+    const size_t need = static_cast<size_t>(p.splits) * M * N * sizeof(float);
+    if (!workspace || workspace_bytes < need) return BD_ERR_WORKSPACE;
+    BD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
+    partial = static_cast<float*>(workspace);
+  }
+  CUtensorMap ta, tw;
+  int rc = make_tmap_2d_bf16(&ta, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda),
+                             kGemmBK, kGemmBM);
+  if (rc != BD_OK) return rc;
+  rc = make_tmap_2d_bf16(&tw, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw),
+                         kGemmBK, static_cast<uint32_t>(p.bn));
+  if (rc != BD_OK) return rc;
+
+  GemmEpi epi;
+  epi.bias = static_cast<const __nv_bfloat16*>(e->bias);
+  epi.gate = static_cast<const __nv_bfloat16*>(e->gate);
+  epi.res = e->res;
+  epi.out = e->out;
+  epi.ld_gate = e->ld_gate;
+  epi.ld_res = e->ld_res;
+  epi.ld_out = e->ld_out;
+  epi.act = e->act;
+  epi.swiglu = e->swiglu;
+  epi.res_f32 = e->res_f32;
+  epi.out_f32 = e->out_f32;
+  const bool pdl = (flags & 1) != 0;
+  switch (p.bn) {
+    case 64: rc = launch_gemm<64>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream); break;
+    case 128: rc = launch_gemm<128>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream); break;
+    default: rc = launch_gemm<256>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream); break;
+  }
+  if (rc != BD_OK) return rc;
+  if (p.splits > 1) {
+    const long long work = static_cast<long long>(M) * ((N + 31) / 32);
+    dim3 grid(static_cast<unsigned>((work + 255) / 256));
+    LaunchCfg lc(grid, dim3(256), 0, stream, pdl);
+    BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, bd_splitk_epilogue_kernel, static_cast<const float*>(partial), M, N,
+                                   p.splits, epi));
+  }
+  return BD_OK;
+}
+
+int bd_interleave16(const void* gate, const void* up, void* out, int F, int K, const void* bias_gate,
+                    const void* bias_up, void* bias_out, bd_stream_t stream) {
+  BD_REQUIRE(gate && up && out && F > 0 && K > 0 && (F % 16) == 0);
+  BD_REQUIRE(!bias_out || (bias_gate && bias_up));
+  bd_interleave16_kernel<<<2 * F, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(gate), static_cast<const __nv_bfloat16*>(up), static_cast<__nv_bfloat16*>(out),
+      F, K, static_cast<const __nv_bfloat16*>(bias_gate), static_cast<const __nv_bfloat16*>(bias_up),
+      static_cast<__nv_bfloat16*>(bias_out));
+  BD_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+}  // extern "C"

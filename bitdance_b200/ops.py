@@ -1,0 +1,150 @@
+"""Python wrappers over the C ABI: one function per ``bd_*`` entry point (device pointers in, status out)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmEpilogue, check, ptr, require_cuda, stream_ptr
+
+ACT = {None: 0, "none": 0, "silu": 1, "gelu_tanh": 2, "gelu_pytorch_tanh": 2}
+
+
+class Workspace:
+    """Grow-only device scratch buffer (owned by torch) handed to C calls that need one."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes: int) -> torch.Tensor | None:
+        if nbytes <= 0:
+            return None
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+_workspaces: dict = {}
+
+
+def default_workspace(device) -> Workspace:
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _workspaces:
+        _workspaces[key] = Workspace(torch.device("cuda", key))
+    return _workspaces[key]
+
+
+def gemm(
+    a: torch.Tensor,
+    w: torch.Tensor,
+    *,
+    bias: torch.Tensor | None = None,
+    act: str | None = None,
+    swiglu: bool = False,
+    gate: torch.Tensor | None = None,
+    res: torch.Tensor | None = None,
+    out: torch.Tensor | None = None,
+    out_dtype: torch.dtype = torch.bfloat16,
+    bn: int = 0,
+    splits: int = 0,
+    pdl: bool = False,
+    workspace: Workspace | None = None,
+) -> torch.Tensor:
+    """``epilogue(a @ w.T)`` — a [M,K] bf16, w [N,K] bf16 (nn.Linear layout); see ``bd_gemm_bf16``."""
+    lib = _lib.load()
+    require_cuda(a, w, bias, gate, res, out)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if swiglu else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    epi = GemmEpilogue()
+    epi.bias = bias.data_ptr() if bias is not None else 0
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.numel() == N and bias.is_contiguous()
+    epi.gate = gate.data_ptr() if gate is not None else 0
+    epi.ld_gate = gate.stride(0) if gate is not None else 0
+    if gate is not None:
+        assert gate.dtype == torch.bfloat16 and gate.shape == (M, N) and gate.stride(1) == 1
+    epi.res = res.data_ptr() if res is not None else 0
+    epi.ld_res = res.stride(0) if res is not None else 0
+    epi.res_f32 = 0
+    if res is not None:
+        assert res.shape == (M, N) and res.stride(1) == 1 and res.dtype in (torch.bfloat16, torch.float32)
+        epi.res_f32 = 1 if res.dtype == torch.float32 else 0
+    epi.out = out.data_ptr()
+    epi.ld_out = out.stride(0)
+    epi.act = ACT[act]
+    epi.swiglu = 1 if swiglu else 0
+    epi.out_f32 = 1 if out.dtype == torch.float32 else 0
+    ws_bytes = lib.bd_gemm_workspace_bytes(M, N, K, bn, splits)
+    ws = (workspace or default_workspace(a.device)).get(ws_bytes)
+    st = lib.bd_gemm_bf16(
+        ptr(a), C.c_int64(a.stride(0)), ptr(w), C.c_int64(w.stride(0)), M, N, K, C.byref(epi), ptr(ws),
+        C.c_size_t(ws.numel() if ws is not None else 0), bn, splits, 1 if pdl else 0, stream_ptr(),
+    )
+    check(st, "bd_gemm_bf16")
+    return out
+
+
+def interleave16(gate_w: torch.Tensor, up_w: torch.Tensor, gate_b=None, up_b=None):
+    """One-time SwiGLU weight re-layout (see ``bd_interleave16``). Returns (w_interleaved, bias_interleaved|None)."""
+    lib = _lib.load()
+    require_cuda(gate_w, up_w)
+    assert gate_w.shape == up_w.shape and gate_w.dtype == torch.bfloat16 and up_w.dtype == torch.bfloat16
+    gate_w, up_w = gate_w.contiguous(), up_w.contiguous()
+    F, K = gate_w.shape
+    out = torch.empty((2 * F, K), dtype=torch.bfloat16, device=gate_w.device)
+    bout = None
+    if gate_b is not None:
+        gate_b, up_b = gate_b.to(torch.bfloat16).contiguous(), up_b.to(torch.bfloat16).contiguous()
+        bout = torch.empty((2 * F,), dtype=torch.bfloat16, device=gate_w.device)
+    check(lib.bd_interleave16(ptr(gate_w), ptr(up_w), ptr(out), F, K, ptr(gate_b), ptr(up_b), ptr(bout), stream_ptr()),
+          "bd_interleave16")
+    return out, bout
+
+
+def sign_pack_nchw(h: torch.Tensor, *, want_quant=True, want_packed=True, num_codebooks: int = 0):
+    """``VQModel.encode`` quantiser (+ packed bits, + GFQ indices). h: [B,C,H,W] fp32/bf16 contiguous."""
+    lib = _lib.load()
+    require_cuda(h)
+    assert h.dim() == 4 and h.is_contiguous() and h.dtype in (torch.float32, torch.bfloat16)
+    B, Cc, H, W = h.shape
+    HW = H * W
+    quant = torch.empty_like(h) if want_quant else None
+    packed = torch.empty((B, HW, Cc // 32), dtype=torch.int32, device=h.device) if want_packed else None
+    idx = torch.empty((num_codebooks, B * HW), dtype=torch.int32, device=h.device) if num_codebooks else None
+    check(lib.bd_sign_pack_nchw(ptr(h), 1 if h.dtype == torch.float32 else 0, B, Cc, HW, ptr(quant), ptr(packed),
+                                ptr(idx), num_codebooks, stream_ptr()), "bd_sign_pack_nchw")
+    return quant, packed, idx
+
+
+def sign_tokens(x: torch.Tensor, *, want_tokens=True, want_packed=True):
+    """``torch.sign`` on the AR path + packed bits. x: [..., C] fp32 contiguous."""
+    lib = _lib.load()
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    tokens = torch.empty_like(x) if want_tokens else None
+    packed = torch.empty((*x.shape[:-1], Cc // 32), dtype=torch.int32, device=x.device) if want_packed else None
+    check(lib.bd_sign_tokens(ptr(x), C.c_longlong(rows), Cc, ptr(tokens), ptr(packed), stream_ptr()), "bd_sign_tokens")
+    return tokens, packed
+
+
+def unpack_tokens(packed: torch.Tensor, C_bits: int, dtype=torch.float32):
+    lib = _lib.load()
+    require_cuda(packed)
+    assert packed.dtype == torch.int32 and packed.is_contiguous() and packed.shape[-1] == C_bits // 32
+    rows = packed.numel() // (C_bits // 32)
+    out = torch.empty((*packed.shape[:-1], C_bits), dtype=dtype, device=packed.device)
+    check(lib.bd_unpack_tokens(ptr(packed), C.c_longlong(rows), C_bits, ptr(out), 1 if dtype == torch.float32 else 0,
+                               stream_ptr()), "bd_unpack_tokens")
+    return out

@@ -1,0 +1,75 @@
+"""Import the UNMODIFIED reference from /root/reference (dev container only) with the three oracle-side shims of
+SURVEY.md §8c. TEST INFRASTRUCTURE ONLY. Used to pin the oracle restatements and to generate tests/golden/*.
+
+Shims (none alters arithmetic):
+  A  flash_attn_func -> eager softmax attention in [B,S,H,D] layout (flash_attn has no CPU backend)
+  B  DynamicCache.__getitem__ -> (keys, values) of a layer (transformers 5.x dropped tuple indexing)
+  C  sdpa attention: slice a 4-D mask to the key length (the reference reuses the cond-sized all-ones mask)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+REF = "/root/reference"
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF, "modeling"))
+
+
+def _eager_flash(q, k, v, causal=False):
+    assert not causal
+    scale = q.shape[-1] ** -0.5
+    qh, kh, vh = (t.transpose(1, 2) for t in (q, k, v))
+    a = torch.softmax((qh * scale) @ kh.transpose(-1, -2), dim=-1)
+    return (a @ vh).transpose(1, 2).contiguous()
+
+
+_done = False
+
+
+def import_reference():
+    """Returns a namespace with the reference modules; applies the shims once."""
+    global _done
+    if not available():
+        raise RuntimeError("/root/reference not present")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import types
+
+    if not _done:
+        # shim A must be in place before flow_head_parallel_x is imported on a box without flash_attn CPU kernels
+        try:
+            import flash_attn  # noqa: F401
+        except Exception:
+            m = types.ModuleType("flash_attn")
+            m.flash_attn_func = _eager_flash
+            sys.modules["flash_attn"] = m
+    import modeling.vision_head.flow_head_parallel_x as fh
+    import modeling.vision_head.sampling_x as sx
+    import modeling.vision_encoder.autoencoder as ae
+    import modeling.utils as mu
+    import modeling.t2i_pipeline as t2i
+
+    if not _done:
+        fh.flash_attn_func = _eager_flash
+        from transformers import DynamicCache
+        from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+
+        if not hasattr(DynamicCache, "_bd_shim"):
+            DynamicCache.__getitem__ = lambda s, i: (s.layers[i].keys, s.layers[i].values)
+            DynamicCache._bd_shim = True
+            _orig = ALL_ATTENTION_FUNCTIONS["sdpa"]
+
+            def _sdpa(module, q, k, v, attention_mask=None, **kw):
+                if attention_mask is not None and attention_mask.dim() == 4:
+                    attention_mask = attention_mask[..., : k.shape[-2]]
+                return _orig(module, q, k, v, attention_mask=attention_mask, **kw)
+
+            ALL_ATTENTION_FUNCTIONS["sdpa"] = _sdpa
+        _done = True
+    ns = types.SimpleNamespace(fh=fh, sx=sx, ae=ae, mu=mu, t2i=t2i)
+    return ns

@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (dev container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+
+    has_gpu = torch.cuda.is_available()
+    has_ref = os.path.isdir("/root/reference/modeling")
+    skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    skip_ref = pytest.mark.skip(reason="/root/reference not present")
+    for item in items:
+        if "gpu" in item.keywords and not has_gpu:
+            item.add_marker(skip_gpu)
+        if "reference" in item.keywords and not has_ref:
+            item.add_marker(skip_ref)
