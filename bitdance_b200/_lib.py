@@ -31,6 +31,7 @@ class GemmEpilogue(C.Structure):
         ("swiglu", C.c_int),
         ("res_f32", C.c_int),
         ("out_f32", C.c_int),
+        ("res_row_mod", C.c_int),
     ]
 
 

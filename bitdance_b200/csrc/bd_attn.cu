@@ -33,6 +33,8 @@ struct AttnParams {
   float* part_o;  // [splits][B][Hq][Sq][D] fp32 (unnormalised) when splits > 1
   float* part_ml; // [splits][B][Hq][Sq][2] (max, sum)
   int B, Sq, Sk, Hq, Hkv;
+  const int* sk_dev;  // optional per-sequence key counts (device): Sk_b = sk_dev[b] + sk_add; Sk = planning bound
+  int sk_add;
   int causal;      // key j visible to query i iff j <= i + (Sk - Sq)
   int splits;
   float scale_log2;  // softmax scale * log2(e)
@@ -96,11 +98,12 @@ __global__ void __launch_bounds__(128) bd_attn_kernel(AttnParams p) {
   const int g = lane >> 2, t = lane & 3;
   const int q0 = qt * 64;
   const int q_valid = min(64, p.Sq - q0);
+  const int Sk = p.sk_dev ? p.sk_dev[b] + p.sk_add : p.Sk;
 
   load_tile<HD>(sQ, p.q + b * p.q_sb + static_cast<long long>(q0) * p.q_ss + h * p.q_sh, p.q_ss, q_valid);
 
   // KV tile range of this split
-  const int n_tiles = (p.Sk + 63) / 64;
+  const int n_tiles = (Sk + 63) / 64;
   const int t_begin = static_cast<int>((static_cast<long long>(split) * n_tiles) / p.splits);
   const int t_end = static_cast<int>((static_cast<long long>(split + 1) * n_tiles) / p.splits);
 
@@ -112,11 +115,11 @@ __global__ void __launch_bounds__(128) bd_attn_kernel(AttnParams p) {
   float m_run[2] = {-FLT_MAX, -FLT_MAX};
   float l_run[2] = {0.f, 0.f};
   const int qrow[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
-  const int causal_off = p.Sk - p.Sq;
+  const int causal_off = Sk - p.Sq;
 
   for (int kt = t_begin; kt < t_end; ++kt) {
     const int k0 = kt * 64;
-    const int k_valid = min(64, p.Sk - k0);
+    const int k_valid = min(64, Sk - k0);
     __syncthreads();  // previous tile fully consumed (also orders the Q store on the first iteration)
     if (p.paged) {
       const int page = p.page_table[b * p.max_pages + kt];
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(128) bd_attn_kernel(AttnParams p) {
       for (int i = 0; i < 4; ++i) {
         const int key = k0 + 8 * j + 2 * t + (i & 1);
         const int r = i >> 1;
-        bool ok = key < p.Sk;
+        bool ok = key < Sk;
         if (p.causal) ok = ok && (key <= qrow[r] + causal_off);
         const float v = ok ? s[j][i] * p.scale_log2 : -FLT_MAX;
         s[j][i] = v;
@@ -316,6 +319,71 @@ int attn_run(AttnParams p, int head_dim, bool pdl, cudaStream_t stream) {
   if (head_dim == 128) return launch_attn<128>(p, pdl, stream);
   if (head_dim == 64) return launch_attn<64>(p, pdl, stream);
   return BD_ERR_UNSUPPORTED;
+}
+
+// LLM attention over the paged cache: q [R*S, Hq*hd] (token-major), pools [page][Hkv][64][hd], out [R*S, Hq*hd].
+// Keys visible to sequence b: sk_dev[b] + S (past + the block just appended).
+size_t attn_llm_workspace_bytes(int R, int S, int Hq, int head_dim, int splits) {
+  if (splits <= 1) return 0;
+  return static_cast<size_t>(splits) * R * Hq * S * (head_dim + 2) * sizeof(float);
+}
+int attn_run_llm(const __nv_bfloat16* q, const __nv_bfloat16* kpool, const __nv_bfloat16* vpool, const int* page_table,
+                 int max_pages, const int* sk_dev, int sk_bound, __nv_bfloat16* out, int R, int S, int Hq, int Hkv,
+                 int head_dim, int causal, int splits, void* ws, size_t ws_bytes, bool pdl, cudaStream_t stream) {
+  AttnParams p{};
+  p.q = q;
+  p.q_sb = static_cast<long long>(S) * Hq * head_dim;
+  p.q_ss = static_cast<long long>(Hq) * head_dim;
+  p.q_sh = head_dim;
+  p.k = kpool;
+  p.v = vpool;
+  p.page_table = page_table;
+  p.max_pages = max_pages;
+  p.paged = 1;
+  p.out = out;
+  p.o_sb = p.q_sb;
+  p.o_ss = p.q_ss;
+  p.o_sh = head_dim;
+  p.B = R;
+  p.Sq = S;
+  p.Sk = sk_bound;
+  p.sk_dev = sk_dev;
+  p.sk_add = S;
+  p.Hq = Hq;
+  p.Hkv = Hkv;
+  p.causal = causal;
+  p.splits = splits;
+  p.scale_log2 = (1.0f / sqrtf(static_cast<float>(head_dim))) * 1.4426950408889634f;
+  if (splits > 1) {
+    const size_t need = attn_llm_workspace_bytes(R, S, Hq, head_dim, splits);
+    if (!ws || ws_bytes < need) return BD_ERR_WORKSPACE;
+    p.part_o = static_cast<float*>(ws);
+    p.part_ml = p.part_o + static_cast<size_t>(splits) * R * Hq * S * head_dim;
+  }
+  return attn_run(p, head_dim, pdl, stream);
+}
+
+// Head attention: qkv [R*pn, 3D] (q | k | v along the last dim, heads of head_dim inside each), out [R*pn, D].
+int attn_run_head(const __nv_bfloat16* qkv, __nv_bfloat16* out, int R, int pn, int D, int head_dim, bool pdl,
+                  cudaStream_t stream) {
+  AttnParams p{};
+  p.q = qkv;
+  p.k = qkv + D;
+  p.v = qkv + 2 * D;
+  p.q_sb = p.k_sb = static_cast<long long>(pn) * 3 * D;
+  p.q_ss = p.k_ss = 3ll * D;
+  p.q_sh = p.k_sh = head_dim;
+  p.out = out;
+  p.o_sb = static_cast<long long>(pn) * D;
+  p.o_ss = D;
+  p.o_sh = head_dim;
+  p.B = R;
+  p.Sq = p.Sk = pn;
+  p.Hq = p.Hkv = D / head_dim;
+  p.causal = 0;
+  p.splits = 1;
+  p.scale_log2 = (1.0f / sqrtf(static_cast<float>(head_dim))) * 1.4426950408889634f;
+  return attn_run(p, head_dim, pdl, stream);
 }
 
 }  // namespace bd

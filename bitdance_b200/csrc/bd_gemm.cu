@@ -60,28 +60,20 @@ __global__ void bd_interleave16_kernel(const __nv_bfloat16* __restrict__ gate, c
   if (threadIdx.x == 0 && bo) bo[r] = (w < 16 ? bg : bu)[src];
 }
 
-}  // namespace bd
-
-using namespace bd;
-
-extern "C" {
-
-size_t bd_gemm_workspace_bytes(int M, int N, int K, int bn, int splits) {
+size_t gemm_workspace_bytes(int M, int N, int K, int bn, int splits) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   GemmPlan p = plan_gemm(M, N, K, bn, splits);
   return p.splits > 1 ? static_cast<size_t>(p.splits) * M * N * sizeof(float) : 0;
 }
 
-int bd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
-                 const bd_gemm_epilogue_t* e, void* workspace, size_t workspace_bytes, int bn, int splits, int flags,
-                 bd_stream_t stream_) {
-  BD_REQUIRE(A && W && e && e->out);
+int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const GemmEpi& epi,
+              void* workspace, size_t workspace_bytes, int bn, int splits, bool pdl, cudaStream_t stream) {
+  BD_REQUIRE(A && W && epi.out);
   BD_REQUIRE(M > 0 && N > 0 && K > 0);
   BD_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 256);
   BD_REQUIRE(splits >= 0);
   BD_REQUIRE(lda >= K && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0);
-  BD_REQUIRE(!e->swiglu || ((N % 32) == 0 && !e->gate && !e->res && !e->out_f32 && e->act == 0));
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BD_REQUIRE(!epi.swiglu || ((N % 32) == 0 && !epi.gate && !epi.res && !epi.out_f32 && epi.act == 0));
   GemmPlan p = plan_gemm(M, N, K, bn, splits);
   float* partial = nullptr;
   if (p.splits > 1) {
@@ -97,20 +89,6 @@ int bd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, 
   rc = make_tmap_2d_bf16(&tw, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw),
                          kGemmBK, static_cast<uint32_t>(p.bn));
   if (rc != BD_OK) return rc;
-
-  GemmEpi epi;
-  epi.bias = static_cast<const __nv_bfloat16*>(e->bias);
-  epi.gate = static_cast<const __nv_bfloat16*>(e->gate);
-  epi.res = e->res;
-  epi.out = e->out;
-  epi.ld_gate = e->ld_gate;
-  epi.ld_res = e->ld_res;
-  epi.ld_out = e->ld_out;
-  epi.act = e->act;
-  epi.swiglu = e->swiglu;
-  epi.res_f32 = e->res_f32;
-  epi.out_f32 = e->out_f32;
-  const bool pdl = (flags & 1) != 0;
   switch (p.bn) {
     case 64: rc = launch_gemm<64>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream); break;
     case 128: rc = launch_gemm<128>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream); break;
@@ -125,6 +103,37 @@ int bd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, 
                                    p.splits, epi));
   }
   return BD_OK;
+}
+
+}  // namespace bd
+
+using namespace bd;
+
+extern "C" {
+
+size_t bd_gemm_workspace_bytes(int M, int N, int K, int bn, int splits) {
+  return gemm_workspace_bytes(M, N, K, bn, splits);
+}
+
+int bd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                 const bd_gemm_epilogue_t* e, void* workspace, size_t workspace_bytes, int bn, int splits, int flags,
+                 bd_stream_t stream_) {
+  BD_REQUIRE(A && W && e && e->out);
+  GemmEpi epi;
+  epi.bias = static_cast<const __nv_bfloat16*>(e->bias);
+  epi.gate = static_cast<const __nv_bfloat16*>(e->gate);
+  epi.res = e->res;
+  epi.out = e->out;
+  epi.ld_gate = e->ld_gate;
+  epi.ld_res = e->ld_res;
+  epi.ld_out = e->ld_out;
+  epi.act = e->act;
+  epi.swiglu = e->swiglu;
+  epi.res_f32 = e->res_f32;
+  epi.out_f32 = e->out_f32;
+  epi.res_mod = e->res_row_mod;
+  return gemm_bf16(A, lda, W, ldw, M, N, K, epi, workspace, workspace_bytes, bn, splits, (flags & 1) != 0,
+                   static_cast<cudaStream_t>(stream_));
 }
 
 int bd_interleave16(const void* gate, const void* up, void* out, int F, int K, const void* bias_gate,

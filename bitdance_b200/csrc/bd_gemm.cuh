@@ -15,30 +15,10 @@
 //     BEFORE griddepcontrol.wait, keeping HBM busy across kernel boundaries.
 #pragma once
 #include <cstdio>
+#include "bd_host.h"
 #include "bd_ptx.cuh"
 
 namespace bd {
-
-enum : int { kActNone = 0, kActSilu = 1, kActGeluTanh = 2 };
-
-// Generic epilogue. Rounding points mirror torch autocast(bf16): every Linear output is rounded to bf16,
-// every bf16 elementwise op rounds again.
-//   y = bf16(acc + bias[n])
-//   act:     y = bf16(act(y))
-//   swiglu:  (W rows interleaved in groups of 16: 16 gate rows then 16 up rows) y = bf16(bf16(silu(g)) * u)
-//   gate:    y = bf16(y * gate[m, n])
-//   res:     y = res[m, n] + y            (rounded to bf16 when the output is bf16)
-struct GemmEpi {
-  const __nv_bfloat16* bias;  // [N] or nullptr
-  const __nv_bfloat16* gate;  // [M, ld_gate] or nullptr
-  const void* res;            // [M, ld_res] bf16 or fp32, or nullptr
-  void* out;                  // [M, ld_out] bf16 or fp32
-  long long ld_gate, ld_res, ld_out;
-  int act;
-  int swiglu;
-  int res_f32;
-  int out_f32;
-};
 
 // Apply the epilogue to 32 consecutive accumulator columns [n0, n0+32) of row m.
 __device__ __forceinline__ void epi_apply_store(const GemmEpi& e, const float (&acc)[32], int m, int n0, int N) {
@@ -79,10 +59,11 @@ __device__ __forceinline__ void epi_apply_store(const GemmEpi& e, const float (&
     if (e.act == kActGeluTanh) v = bf16_round(gelu_tanhf_(v));
     if (e.gate && ok) v = bf16_round(v * __bfloat162float(e.gate[static_cast<long long>(m) * e.ld_gate + n]));
     if (e.res && ok) {
+      const long long mr = e.res_mod > 0 ? (m % e.res_mod) : m;
       if (e.res_f32)
-        v += reinterpret_cast<const float*>(e.res)[static_cast<long long>(m) * e.ld_res + n];
+        v += reinterpret_cast<const float*>(e.res)[mr * e.ld_res + n];
       else
-        v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.res)[static_cast<long long>(m) * e.ld_res + n]);
+        v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.res)[mr * e.ld_res + n]);
     }
     y[j] = v;
   }

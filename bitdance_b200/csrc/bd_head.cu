@@ -1,0 +1,520 @@
+// bd_head.cu — the binary-diffusion vision head: x-prediction transformer + Euler–Maruyama sampler, one C call.
+//
+// Replaces, per AR step, DiffHead.sample -> euler_maruyama (modeling/vision_head/sampling_x.py:44-97) driving
+// TransEncoder.forward (modeling/vision_head/flow_head_parallel_x.py:325-342) S+1 times. Every Linear goes through the
+// tcgen05 weight-streaming GEMM (bd_gemm.cuh) with the surrounding elementwise work fused in its epilogue; what is
+// left are the small HBM/L2-resident kernels in this file. Exact restructurings (do not change results):
+//   * cond_embed(c) is evaluated once per sample() call instead of S+1 times (c is constant across evaluations);
+//   * time_embed(t) is evaluated for all S+1 timesteps in one batched GEMM (t is the same for every row);
+//   * the 2 adaLN Linears and final_layer.ada_ln_modulation share their input y: one GEMM over concatenated weights;
+//   * the rows of cat([x, x]) (cond | uncond halves, sampling_x.py:71) are written once and duplicated.
+// Noise is an input (drawn by torch in the reference's call order), so the sampler itself is deterministic.
+#include "bd_host.h"
+#include "bd_ptx.cuh"
+
+namespace bd {
+
+int attn_run_head(const __nv_bfloat16* qkv, __nv_bfloat16* out, int R, int pn, int D, int head_dim, bool pdl,
+                  cudaStream_t stream);  // bd_attn.cu
+
+// ---------------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? red[l] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+// timestep_embedding (flow_head_parallel_x.py:12-27): [cos(1000 t f_k) | sin(1000 t f_k)], f_k = exp(-ln(1e4) k/half),
+// fp32 math, written as bf16 (it only feeds a Linear under autocast).
+struct TVals {
+  float t[128];
+};
+__global__ void timestep_embedding_kernel(TVals tv_, int row0, int dim, __nv_bfloat16* __restrict__ out) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int i = row0 + blockIdx.x;
+  const int half = dim / 2;
+  const float tv = 1000.0f * tv_.t[blockIdx.x];
+  for (int k = threadIdx.x; k < half; k += blockDim.x) {
+    const float f = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+    const float a = tv * f;
+    out[static_cast<long long>(i) * dim + k] = __float2bfloat16_rn(cosf(a));
+    out[static_cast<long long>(i) * dim + half + k] = __float2bfloat16_rn(sinf(a));
+  }
+}
+
+// fp32 -> bf16 cast of a [rows, cols] matrix (the autocast input cast of cond_embed / MLPconnector).
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + i) = pk;
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+
+// y[m, :] = bf16(silu(bf16(t_emb[:] + c_emb[m, :])))      (TransEncoder.forward :330: y = F.silu(t + c))
+__global__ void silu_add_kernel(const __nv_bfloat16* __restrict__ t_emb, const __nv_bfloat16* __restrict__ c_emb,
+                                __nv_bfloat16* __restrict__ y, int M, int D) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i >= static_cast<long long>(M) * D) return;
+  const int d = static_cast<int>(i % D);
+  const uint4 tv = *reinterpret_cast<const uint4*>(t_emb + d);
+  const uint4 cv = *reinterpret_cast<const uint4*>(c_emb + i);
+  const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&tv);
+  const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cv);
+  uint4 ov;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = __bfloat1622float2(t2[j]), b = __bfloat1622float2(c2[j]);
+    const float s0 = bf16_round(a.x + b.x), s1 = bf16_round(a.y + b.y);
+    o2[j] = __floats2bfloat162_rn(siluf_(s0), siluf_(s1));
+  }
+  *reinterpret_cast<uint4*>(y + i) = ov;
+}
+
+// out[m,:] = bf16( LN(x[m,:]) (*w + b) * bf16(1 + scale[m,:]) + shift[m,:] )     (TransBlock.forward :243,246;
+// FinalLayer.forward :171). LN statistics in fp32 (autocast runs layer_norm in fp32), eps 1e-6.
+// One CTA per row, 256 threads, the row cached in registers (D <= 8192, D % 8 == 0).
+constexpr int kLnThreads = 256;
+constexpr int kLnMaxVec = 4;
+__global__ void __launch_bounds__(kLnThreads) layernorm_mod_kernel(
+    const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ w, const float* __restrict__ b,
+    const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift, long long ld_mod,
+    __nv_bfloat16* __restrict__ out, long long ldo, int D, float eps) {
+  __shared__ float red[32];
+  grid_dep_launch();
+  grid_dep_wait();
+  const int m = blockIdx.x;
+  const int nvec = D / 8;
+  float v[kLnMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = threadIdx.x + i * kLnThreads;
+    if (c < nvec) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(x + m * ldx + c * 8);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(p[j]);
+        v[i][2 * j] = f.x;
+        v[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+  const float mean = block_sum(sum, red) / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = threadIdx.x + i * kLnThreads;
+    if (c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / static_cast<float>(D) + eps);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = threadIdx.x + i * kLnThreads;
+    if (c < nvec) {
+      const uint4 sraw = *reinterpret_cast<const uint4*>(scale + m * ld_mod + c * 8);
+      const uint4 hraw = *reinterpret_cast<const uint4*>(shift + m * ld_mod + c * 8);
+      const __nv_bfloat16* sc = reinterpret_cast<const __nv_bfloat16*>(&sraw);
+      const __nv_bfloat16* sh = reinterpret_cast<const __nv_bfloat16*>(&hraw);
+      uint4 ov;
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float h = (v[i][j] - mean) * rstd;
+        if (w) h = h * w[c * 8 + j] + b[c * 8 + j];
+        const float one_plus = bf16_round(1.0f + __bfloat162float(sc[j]));
+        o[j] = __float2bfloat16_rn(h * one_plus + __bfloat162float(sh[j]));
+      }
+      *reinterpret_cast<uint4*>(out + m * ldo + c * 8) = ov;
+    }
+  }
+}
+
+// FinalLayer (flow_head_parallel_x.py:169-173) + output map (:341-342), one CTA per token row:
+//   h = bf16(LN(x) * bf16(1+scale) + shift);  o_c = bf16(sum_d h_d W[c,d] + bias_c);
+//   pred_c = out_sigmoid ? bf16(bf16(2 * bf16(sigmoid(o_c))) - 1) : o_c          -> fp32 [M, C]
+__global__ void __launch_bounds__(256) head_final_kernel(const __nv_bfloat16* __restrict__ x, int D,
+                                                         const __nv_bfloat16* __restrict__ scale,
+                                                         const __nv_bfloat16* __restrict__ shift, long long ld_mod,
+                                                         const __nv_bfloat16* __restrict__ Wf,
+                                                         const __nv_bfloat16* __restrict__ bf, int C, int out_sigmoid,
+                                                         float eps, float* __restrict__ pred) {
+  extern __shared__ float hrow[];  // [D]
+  __shared__ float red[32];
+  grid_dep_launch();
+  grid_dep_wait();
+  const int m = blockIdx.x;
+  float sum = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float f = __bfloat162float(x[static_cast<long long>(m) * D + d]);
+    hrow[d] = f;
+    sum += f;
+  }
+  const float mean = block_sum(sum, red) / static_cast<float>(D);
+  float sq = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float t = hrow[d] - mean;
+    sq += t * t;
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / static_cast<float>(D) + eps);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float one_plus = bf16_round(1.0f + __bfloat162float(scale[m * ld_mod + d]));
+    hrow[d] = bf16_round((hrow[d] - mean) * rstd * one_plus + __bfloat162float(shift[m * ld_mod + d]));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < C; c += (blockDim.x >> 5)) {
+    const __nv_bfloat16* wr = Wf + static_cast<long long>(c) * D;
+    float acc = 0.f;
+    for (int d = lane * 8; d < D; d += 256) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(wr + d);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(p[j]);
+        acc = fmaf(hrow[d + 2 * j], f.x, acc);
+        acc = fmaf(hrow[d + 2 * j + 1], f.y, acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float o = bf16_round(acc + (bf ? __bfloat162float(bf[c]) : 0.f));
+      if (out_sigmoid) {
+        const float s = bf16_round(1.0f / (1.0f + expf(-o)));
+        o = bf16_round(bf16_round(2.0f * s) - 1.0f);
+      }
+      pred[static_cast<long long>(m) * C + c] = o;
+    }
+  }
+}
+
+// One Euler–Maruyama step (sampling_x.py:33-41) or the last deterministic Euler step (:24-30), fp32, written with
+// explicit round-to-nearest intrinsics so that nvcc cannot contract a*b+c: each torch op rounds separately.
+struct SdeStep {
+  float t, dt, denom, var, one_minus_t, noise_scale;
+  float cfg;
+  int cfg_mult;
+  int last;
+};
+__global__ void sde_step_kernel(float* __restrict__ x, const float* __restrict__ pred, const float* __restrict__ noise,
+                                int n, SdeStep s, __nv_bfloat16* __restrict__ xb) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float xv = x[i];
+  float v = __fdiv_rn(__fsub_rn(pred[i], xv), s.denom);  // v = (output - combined) / clamp(1 - t, 0.05)
+  if (s.cfg_mult == 2) {
+    const float vu = __fdiv_rn(__fsub_rn(pred[n + i], xv), s.denom);
+    v = __fadd_rn(vu, __fmul_rn(s.cfg, __fsub_rn(v, vu)));  // uncond + cfg * (cond - uncond)
+  }
+  float xn;
+  if (s.last) {
+    xn = __fadd_rn(xv, __fmul_rn(v, s.dt));
+  } else {
+    const float score = __fdiv_rn(__fsub_rn(__fmul_rn(s.t, v), xv), s.var);
+    const float drift = __fadd_rn(v, __fmul_rn(s.one_minus_t, score));
+    xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(drift, s.dt)), __fmul_rn(s.noise_scale, noise[i]));
+  }
+  x[i] = xn;
+  if (xb) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(xn);
+    xb[i] = b;
+    if (s.cfg_mult == 2) xb[n + i] = b;
+  }
+}
+
+// x0 = noise[0]; xb = bf16(cat[x0] * mult)
+__global__ void sde_init_kernel(float* __restrict__ x, const float* __restrict__ noise0, int n, int cfg_mult,
+                                __nv_bfloat16* __restrict__ xb) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = noise0[i];
+  x[i] = v;
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  xb[i] = b;
+  if (cfg_mult == 2) xb[n + i] = b;
+}
+
+template <typename... KArgs, typename... Args>
+static int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  LaunchCfg lc(grid, block, smem, st, pdl);
+  BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kern, static_cast<KArgs>(args)...));
+  return BD_OK;
+}
+
+struct HeadWs {
+  // offsets (bytes) into the workspace
+  size_t xb, h, a, o, qkv, g, y, mod, cemb, tfreq, th, temb, pred, x, condb, tvals, gemm, total;
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+static HeadWs head_ws_layout(const bd_head_weights_t& w, int M, int n_rows_x, int S) {
+  HeadWs L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes);
+    return o;
+  };
+  const size_t D = w.D, C = w.C;
+  const int n_mod = w.n_ada * 6 * w.D + 2 * w.D;
+  const size_t wide = 3 * D > static_cast<size_t>(2 * w.hidden) ? 3 * D : 2 * w.hidden;
+  L.xb = take(static_cast<size_t>(M) * C * 2);
+  L.h = take(M * D * 2);
+  L.a = take(M * D * 2);
+  L.o = take(M * D * 2);
+  L.qkv = take(M * wide * 2);
+  L.g = take(static_cast<size_t>(M) * w.hidden * 2);
+  L.y = take(M * D * 2);
+  L.mod = take(static_cast<size_t>(M) * n_mod * 2);
+  L.cemb = take(M * D * 2);
+  L.tfreq = take(static_cast<size_t>(S + 1) * 256 * 2);
+  L.th = take(static_cast<size_t>(S + 1) * D * 2);
+  L.temb = take(static_cast<size_t>(S + 1) * D * 2);
+  L.pred = take(static_cast<size_t>(M) * C * 4);
+  L.x = take(static_cast<size_t>(n_rows_x) * C * 4);
+  L.condb = take(static_cast<size_t>(M) * w.Dz * 2);
+  L.tvals = take(static_cast<size_t>(S + 1) * 4);
+  size_t gm = 0;
+  auto gw = [&](int m, int n, int k) {
+    size_t b = gemm_workspace_bytes(m, n, k, 0, 0);
+    if (b > gm) gm = b;
+  };
+  gw(M, w.D, w.C);
+  gw(S + 1, w.D, 256);
+  gw(S + 1, w.D, w.D);
+  gw(M, w.D, w.Dz);
+  gw(M, n_mod, w.D);
+  gw(M, 3 * w.D, w.D);
+  gw(M, w.D, w.D);
+  gw(M, 2 * w.hidden, w.D);
+  gw(M, w.hidden, w.D);
+  gw(M, w.D, w.hidden);
+  L.gemm = take(gm);
+  L.total = off;
+  return L;
+}
+
+}  // namespace bd
+
+using namespace bd;
+
+extern "C" {
+
+size_t bd_head_workspace_bytes(const bd_head_weights_t* w, int B, int pn, int cfg_mult, int S) {
+  if (!w || B <= 0 || pn <= 0 || cfg_mult < 1 || cfg_mult > 2 || S < 0) return 0;
+  return head_ws_layout(*w, B * cfg_mult * pn, B * pn, S).total;
+}
+
+#define BD_TRY(expr)          \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != BD_OK) return _rc; \
+  } while (0)
+
+int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* noise, const float* sched_host, int B,
+                   int pn, int cfg_mult, float cfg, int S, float* x_out, float* trace, void* workspace,
+                   size_t workspace_bytes, int flags, bd_stream_t stream_) {
+  BD_REQUIRE(wp && cond && noise && sched_host && x_out && workspace);
+  const bd_head_weights_t& w = *wp;
+  BD_REQUIRE(B > 0 && pn > 0 && (cfg_mult == 1 || cfg_mult == 2) && S >= 0);
+  BD_REQUIRE(w.D > 0 && (w.D % 64) == 0 && w.D <= 8192 && w.C > 0 && (w.C % 8) == 0 && w.Dz > 0 && (w.Dz % 8) == 0);
+  BD_REQUIRE(w.n_blocks > 0 && w.n_blocks <= BD_HEAD_MAX_BLOCKS && w.n_ada > 0 && (w.n_blocks % w.n_ada) == 0);
+  BD_REQUIRE(w.head_dim == 64 || w.head_dim == 128);
+  BD_REQUIRE(pn <= 64);  // one KV tile per block of parallel tokens
+  BD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const bool pdl = (flags & 1) != 0;
+  const int R = B * cfg_mult, M = R * pn, nx = B * pn;
+  const int D = w.D, C = w.C;
+  const int n_mod = w.n_ada * 6 * D + 2 * D;
+  const HeadWs L = head_ws_layout(w, M, nx, S);
+  if (workspace_bytes < L.total) return BD_ERR_WORKSPACE;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  auto bfp = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
+  __nv_bfloat16 *xb = bfp(L.xb), *h = bfp(L.h), *a = bfp(L.a), *o = bfp(L.o), *qkv = bfp(L.qkv), *g = bfp(L.g),
+                *y = bfp(L.y), *mod = bfp(L.mod), *cemb = bfp(L.cemb), *tfreq = bfp(L.tfreq), *th = bfp(L.th),
+                *temb = bfp(L.temb), *condb = bfp(L.condb);
+  float* pred = reinterpret_cast<float*>(base + L.pred);
+  float* x = reinterpret_cast<float*>(base + L.x);
+  void* gws = base + L.gemm;
+  const size_t gws_bytes = L.total - L.gemm;
+  const int switch_freq = w.n_blocks / w.n_ada;
+
+  auto gemm = [&](const void* A, long long lda, const void* W, int m, int n, int k, GemmEpi e) {
+    return gemm_bf16(A, lda, W, k, m, n, k, e, gws, gws_bytes, 0, 0, pdl, st);
+  };
+  auto bf = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+
+  // ---- once per call: timestep values -> time embeddings for all S+1 evaluations; cond_embed(c) ----
+  // sched_host rows: [t, dt, denom, var, one_minus_t, noise_scale, _, _]
+  for (int r0 = 0; r0 <= S; r0 += 128) {  // timestep values travel as kernel parameters (graph-capture safe)
+    TVals tv{};
+    const int cnt = (S + 1 - r0) < 128 ? (S + 1 - r0) : 128;
+    for (int i = 0; i < cnt; ++i) tv.t[i] = sched_host[(r0 + i) * 8];
+    BD_TRY(launch(timestep_embedding_kernel, dim3(cnt), dim3(128), 0, st, false, tv, r0, 256, tfreq));
+  }
+  {
+    GemmEpi e;
+    e.bias = bf(w.time0_b);
+    e.act = kActSilu;
+    e.out = th;
+    e.ld_out = D;
+    BD_TRY(gemm(tfreq, 256, w.time0_w, S + 1, D, 256, e));
+    GemmEpi e2;
+    e2.bias = bf(w.time2_b);
+    e2.out = temb;
+    e2.ld_out = D;
+    BD_TRY(gemm(th, D, w.time2_w, S + 1, D, D, e2));
+  }
+  {
+    const long long n = static_cast<long long>(M) * w.Dz;
+    BD_TRY(launch(cast_f32_bf16_kernel, dim3(static_cast<unsigned>((n / 4 + 255) / 256 + 1)), dim3(256), 0, st, pdl,
+                  cond, condb, n));
+    GemmEpi e;
+    e.bias = bf(w.cond_b);
+    e.out = cemb;
+    e.ld_out = D;
+    BD_TRY(gemm(condb, w.Dz, w.cond_w, M, D, w.Dz, e));
+  }
+  const int nel = nx * C;
+  BD_TRY(launch(sde_init_kernel, dim3((nel + 255) / 256), dim3(256), 0, st, pdl, x, noise, nel, cfg_mult, xb));
+
+  // ---- S stochastic evaluations + 1 deterministic ----
+  for (int it = 0; it <= S; ++it) {
+    const float* sc = sched_host + it * 8;
+    {  // h = input_proj(x)
+      GemmEpi e;
+      e.bias = bf(w.input_proj_b);
+      e.out = h;
+      e.ld_out = D;
+      BD_TRY(gemm(xb, C, w.input_proj_w, M, D, C, e));
+    }
+    {  // y = silu(t_emb + c_emb)
+      const long long n = static_cast<long long>(M) * D / 8;
+      BD_TRY(launch(silu_add_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, pdl,
+                    (const __nv_bfloat16*)(temb + static_cast<long long>(it) * D), (const __nv_bfloat16*)cemb, y, M, D));
+    }
+    {  // all adaLN modulations in one GEMM: [ada_0 (6D) | ada_1 (6D) | ... | final (2D)]
+      GemmEpi e;
+      e.bias = bf(w.ada_b);
+      e.out = mod;
+      e.ld_out = n_mod;
+      BD_TRY(gemm(y, D, w.ada_w, M, n_mod, D, e));
+    }
+    for (int blk = 0; blk < w.n_blocks; ++blk) {
+      const bd_head_block_t& bw = w.blocks[blk];
+      const __nv_bfloat16* md = mod + static_cast<long long>(blk / switch_freq) * 6 * D;
+      // chunk order: scale1, shift1, gate1, scale2, shift2, gate2
+      BD_TRY(launch(layernorm_mod_kernel, dim3(M), dim3(kLnThreads), 0, st, pdl, (const __nv_bfloat16*)h,
+                    (long long)D, bw.norm1_w, bw.norm1_b, md, md + D, (long long)n_mod, a, (long long)D, D, 1e-6f));
+      {
+        GemmEpi e;
+        e.bias = bf(bw.wqkv_b);
+        e.out = qkv;
+        e.ld_out = 3 * D;
+        BD_TRY(gemm(a, D, bw.wqkv_w, M, 3 * D, D, e));
+      }
+      BD_TRY(attn_run_head(qkv, o, R, pn, D, w.head_dim, pdl, st));
+      {  // h = h + (wo(o) + b) * gate1
+        GemmEpi e;
+        e.bias = bf(bw.wo_b);
+        e.gate = md + 2 * D;
+        e.ld_gate = n_mod;
+        e.res = h;
+        e.ld_res = D;
+        e.out = h;
+        e.ld_out = D;
+        BD_TRY(gemm(o, D, bw.wo_w, M, D, D, e));
+      }
+      BD_TRY(launch(layernorm_mod_kernel, dim3(M), dim3(kLnThreads), 0, st, pdl, (const __nv_bfloat16*)h,
+                    (long long)D, bw.norm2_w, bw.norm2_b, md + 3 * D, md + 4 * D, (long long)n_mod, a, (long long)D, D,
+                    1e-6f));
+      if (w.use_swiglu) {
+        GemmEpi e;
+        e.bias = bf(bw.w1_b);
+        e.swiglu = 1;
+        e.out = g;
+        e.ld_out = w.hidden;
+        BD_TRY(gemm(a, D, bw.w1_w, M, 2 * w.hidden, D, e));
+      } else {
+        GemmEpi e;
+        e.bias = bf(bw.w1_b);
+        e.act = kActSilu;
+        e.out = g;
+        e.ld_out = w.hidden;
+        BD_TRY(gemm(a, D, bw.w1_w, M, w.hidden, D, e));
+      }
+      {  // h = h + (w2(g) + b) * gate2
+        GemmEpi e;
+        e.bias = bf(bw.w2_b);
+        e.gate = md + 5 * D;
+        e.ld_gate = n_mod;
+        e.res = h;
+        e.ld_res = D;
+        e.out = h;
+        e.ld_out = D;
+        BD_TRY(gemm(g, w.hidden, bw.w2_w, M, D, w.hidden, e));
+      }
+    }
+    {
+      const __nv_bfloat16* mf = mod + static_cast<long long>(w.n_ada) * 6 * D;  // scale | shift
+      BD_TRY(launch(head_final_kernel, dim3(M), dim3(256), static_cast<size_t>(D) * 4, st, pdl, (const __nv_bfloat16*)h,
+                    D, mf, mf + D, (long long)n_mod, bf(w.final_w), bf(w.final_b), C, w.out_sigmoid, 1e-6f, pred));
+    }
+    if (trace)
+      BD_CUDA_TRY(cudaMemcpyAsync(trace + static_cast<long long>(it) * M * C, pred, sizeof(float) * M * C,
+                                  cudaMemcpyDeviceToDevice, st));
+    SdeStep s;
+    s.t = sc[0];
+    s.dt = sc[1];
+    s.denom = sc[2];
+    s.var = sc[3];
+    s.one_minus_t = sc[4];
+    s.noise_scale = sc[5];
+    s.cfg = cfg;
+    s.cfg_mult = cfg_mult;
+    s.last = (it == S) ? 1 : 0;
+    const float* nz = (it < S) ? noise + static_cast<long long>(it + 1) * nel : noise;
+    BD_TRY(launch(sde_step_kernel, dim3((nel + 255) / 256), dim3(256), 0, st, pdl, x, (const float*)pred, nz, nel, s,
+                  (it < S) ? xb : (__nv_bfloat16*)nullptr));
+  }
+  BD_CUDA_TRY(cudaMemcpyAsync(x_out, x, sizeof(float) * nel, cudaMemcpyDeviceToDevice, st));
+  return BD_OK;
+}
+
+}  // extern "C"

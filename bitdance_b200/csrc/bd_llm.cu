@@ -1,0 +1,345 @@
+// bd_llm.cu — Qwen3 decoder stack over a paged KV cache: one C call per forward (prefill chunk or AR block).
+//
+// Replaces the third-party arithmetic the reference calls at modeling/t2i_pipeline.py:199,211,224,229,261,266
+// (transformers Qwen3Model.forward: RMSNorm -> q/k/v -> q/k RMSNorm(head_dim) -> RoPE -> cache update -> SDPA ->
+// o_proj -> +res -> RMSNorm -> SwiGLU -> +res, final RMSNorm). B200-first differences from the reference's execution:
+//   * cond and uncond sequences run in ONE pass (the reference makes two model() calls per AR step, streaming the
+//     26 GB of weights twice); sequences may have different past lengths (device-side seq_lens);
+//   * q/k/v and gate/up weights are fused ([q|k|v] rows; interleave16(gate, up));
+//   * KV lives in 64-token pages (= one parallel block of the 64x model) instead of a torch.cat-grown DynamicCache;
+//     K is stored as bf16(RoPE(k)) — identical to what SDPA consumes under autocast (oracle/llm.py docstring).
+// Rounding policy: oracle/llm.py (stream_f32 = AR steps, else prefill).
+#include "bd_host.h"
+#include "bd_ptx.cuh"
+
+namespace bd {
+
+struct AttnParams;
+int attn_run_llm(const __nv_bfloat16* q, const __nv_bfloat16* kpool, const __nv_bfloat16* vpool, const int* page_table,
+                 int max_pages, const int* sk_dev, int sk_bound, __nv_bfloat16* out, int R, int S, int Hq, int Hkv,
+                 int head_dim, int causal, int splits, void* ws, size_t ws_bytes, bool pdl, cudaStream_t stream);
+size_t attn_llm_workspace_bytes(int R, int S, int Hq, int head_dim, int splits);
+
+__device__ __forceinline__ float block_sum256(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? red[l] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+// Qwen3RMSNorm. x: [M, D] fp32 (IN_F32) or bf16. weight bf16 [D].
+//   fp32 stream: y = float(w) * (x * rstd)                      (fp32; the consumer Linear rounds it to bf16)
+//   bf16 stream: y = bf16(w * bf16(x * rstd))
+// out: bf16 [M, D] (GEMM operand) or, for the final norm, the stream dtype (OUT_F32) with an optional fp32 row table
+// added (add[m % add_mod, :]): h_fused = last_hidden_state + pos_embed (modeling/t2i_pipeline.py:245).
+template <bool IN_F32, bool OUT_F32>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const void* __restrict__ x_, const __nv_bfloat16* __restrict__ w,
+                                                      void* __restrict__ out_, int D, float eps,
+                                                      const float* __restrict__ add, int add_mod) {
+  __shared__ float red[32];
+  grid_dep_launch();
+  grid_dep_wait();
+  const long long m = blockIdx.x;
+  float ss = 0.f;
+  for (int d = threadIdx.x * 4; d < D; d += 256 * 4) {
+    float v[4];
+    if (IN_F32) {
+      const float4 t = *reinterpret_cast<const float4*>(static_cast<const float*>(x_) + m * D + d);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(x_) + m * D + d);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&t);
+      const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    ss += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+  }
+  const float rstd = rsqrtf(block_sum256(ss, red) / static_cast<float>(D) + eps);
+  for (int d = threadIdx.x * 4; d < D; d += 256 * 4) {
+    float v[4];
+    if (IN_F32) {
+      const float4 t = *reinterpret_cast<const float4*>(static_cast<const float*>(x_) + m * D + d);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(x_) + m * D + d);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&t);
+      const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float wf = __bfloat162float(w[d + j]);
+      if (IN_F32)
+        y[j] = wf * (v[j] * rstd);
+      else
+        y[j] = bf16_round(wf * bf16_round(v[j] * rstd));
+      if (add) y[j] += add[static_cast<long long>(m % add_mod) * D + d + j];
+    }
+    if (OUT_F32) {
+      *reinterpret_cast<float4*>(static_cast<float*>(out_) + m * D + d) = make_float4(y[0], y[1], y[2], y[3]);
+    } else {
+      __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]), b = __floats2bfloat162_rn(y[2], y[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out_) + m * D + d) = pk;
+    }
+  }
+}
+
+// q/k RMSNorm over head_dim + RoPE + KV-cache append. One warp per (token, head); head_dim = 32 * VPT.
+//   qkv: bf16 [M, (Hq + 2 Hkv) * hd] rows = [q heads | k heads | v heads]
+//   q_out: bf16 [M, Hq * hd];  K/V pools: [page][Hkv][64][hd];  position of token (b, s) = seq_lens[b] + s
+//   rope tables: fp32 [max_pos, hd] (cos | sin of cat(freqs, freqs), built by torch exactly like Qwen3RotaryEmbedding)
+//   ROPE_F32 (AR steps): rot = q*cos + rotate_half(q)*sin in fp32 (unfused), then bf16 (the SDPA autocast cast)
+//   else (prefill):      cos/sin rounded to bf16, every product and the sum round to bf16
+template <int HD, bool ROPE_F32>
+__global__ void __launch_bounds__(256) qk_norm_rope_append_kernel(
+    const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ qn_w, const __nv_bfloat16* __restrict__ kn_w,
+    const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, const int* __restrict__ seq_lens,
+    const int* __restrict__ page_table, int max_pages, __nv_bfloat16* __restrict__ q_out,
+    __nv_bfloat16* __restrict__ kpool, __nv_bfloat16* __restrict__ vpool, int S, int Hq, int Hkv, float eps, int M) {
+  grid_dep_launch();
+  grid_dep_wait();
+  constexpr int VPT = HD / 32;  // consecutive elements per lane
+  const int heads = Hq + 2 * Hkv;
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= static_cast<long long>(M) * heads) return;
+  const int lane = threadIdx.x & 31;
+  const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
+  const int b = m / S, s = m % S;
+  const int pos = seq_lens[b] + s;
+  const __nv_bfloat16* src = qkv + static_cast<long long>(m) * heads * HD + static_cast<long long>(hh) * HD + lane * VPT;
+  float x[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) x[j] = __bfloat162float(src[j]);
+  const bool is_q = hh < Hq, is_k = !is_q && hh < Hq + Hkv;
+  __nv_bfloat16* dst;
+  if (is_q) {
+    dst = q_out + static_cast<long long>(m) * Hq * HD + static_cast<long long>(hh) * HD;
+  } else {
+    const int hk = is_k ? hh - Hq : hh - Hq - Hkv;
+    const int page = page_table[b * max_pages + pos / 64];
+    dst = (is_k ? kpool : vpool) + ((static_cast<long long>(page) * Hkv + hk) * 64 + (pos % 64)) * HD;
+  }
+  if (!is_q && !is_k) {  // V: plain copy
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) dst[lane * VPT + j] = __float2bfloat16_rn(x[j]);
+    return;
+  }
+  // RMSNorm over the head (bf16 in -> bf16 out): bf16(w * bf16(x * rstd))
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) ss += x[j] * x[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / static_cast<float>(HD) + eps);
+  const __nv_bfloat16* nw = is_q ? qn_w : kn_w;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j)
+    x[j] = bf16_round(__bfloat162float(nw[lane * VPT + j]) * bf16_round(x[j] * rstd));
+  // rotate_half partner: element d pairs with d +- HD/2, i.e. lane +- 16
+  float y[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const float other = __shfl_xor_sync(0xffffffffu, x[j], 16);
+    const float rot = (lane < 16) ? -other : other;  // cat(-x2, x1)
+    const int d = lane * VPT + j;
+    const float c = rope_cos[static_cast<long long>(pos) * HD + d], sn = rope_sin[static_cast<long long>(pos) * HD + d];
+    if (ROPE_F32)
+      y[j] = __fadd_rn(__fmul_rn(x[j], c), __fmul_rn(rot, sn));
+    else
+      y[j] = bf16_round(bf16_round(x[j] * bf16_round(c)) + bf16_round(rot * bf16_round(sn)));
+  }
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) dst[lane * VPT + j] = __float2bfloat16_rn(y[j]);
+}
+
+__global__ void bump_seq_lens_kernel(int* seq_lens, int R, int S) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) seq_lens[i] += S;
+}
+
+template <typename... KArgs, typename... Args>
+static int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  LaunchCfg lc(grid, block, smem, st, pdl);
+  BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kern, static_cast<KArgs>(args)...));
+  return BD_OK;
+}
+
+static size_t al(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct LlmWs {
+  size_t a, qkv, q, o, g, attn, gemm, total;
+};
+
+static LlmWs llm_ws_layout(const bd_llm_weights_t& w, int M, int R, int S, int attn_splits) {
+  LlmWs L{};
+  size_t off = 0;
+  auto take = [&](size_t b) {
+    size_t o = off;
+    off = al(off + b);
+    return o;
+  };
+  const size_t qkv_n = static_cast<size_t>(w.Hq + 2 * w.Hkv) * w.head_dim;
+  L.a = take(static_cast<size_t>(M) * w.D * 2);
+  L.qkv = take(M * qkv_n * 2);
+  L.q = take(static_cast<size_t>(M) * w.Hq * w.head_dim * 2);
+  L.o = take(static_cast<size_t>(M) * w.Hq * w.head_dim * 2);
+  L.g = take(static_cast<size_t>(M) * w.I * 2);
+  L.attn = take(attn_llm_workspace_bytes(R, S, w.Hq, w.head_dim, attn_splits));
+  size_t gm = 0;
+  auto gw = [&](int n, int k) {
+    size_t b = gemm_workspace_bytes(M, n, k, 0, 0);
+    if (b > gm) gm = b;
+  };
+  gw(static_cast<int>(qkv_n), w.D);
+  gw(w.D, w.Hq * w.head_dim);
+  gw(2 * w.I, w.D);
+  gw(w.D, w.I);
+  L.gemm = take(gm);
+  L.total = off;
+  return L;
+}
+
+}  // namespace bd
+
+using namespace bd;
+
+extern "C" {
+
+size_t bd_llm_workspace_bytes(const bd_llm_weights_t* w, int R, int S, int attn_splits) {
+  if (!w || R <= 0 || S <= 0) return 0;
+  return llm_ws_layout(*w, R * S, R, S, attn_splits).total;
+}
+
+#define BD_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != BD_OK) return _rc; \
+  } while (0)
+
+int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int R, int S, int* seq_lens,
+                   int sk_bound, int causal, void* kv_pool, int64_t kv_layer_stride, int64_t kv_v_offset,
+                   const int32_t* page_table, int max_pages, const float* rope_cos, const float* rope_sin, void* out,
+                   const float* out_add, int out_add_mod, int attn_splits, void* workspace, size_t workspace_bytes,
+                   int flags, bd_stream_t stream_) {
+  BD_REQUIRE(wp && hidden && seq_lens && kv_pool && page_table && rope_cos && rope_sin && out && workspace);
+  const bd_llm_weights_t& w = *wp;
+  BD_REQUIRE(R > 0 && S > 0 && w.n_layers > 0 && w.layers);
+  BD_REQUIRE(w.head_dim == 128 || w.head_dim == 64);
+  BD_REQUIRE((w.D % 64) == 0 && (w.I % 64) == 0 && (w.Hq % w.Hkv) == 0);
+  BD_REQUIRE(attn_splits >= 1 && sk_bound >= S && max_pages * 64 >= sk_bound);
+  BD_REQUIRE(!out_add || stream_f32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const bool pdl = (flags & 1) != 0;
+  const int M = R * S, D = w.D, hd = w.head_dim;
+  const int qkv_n = (w.Hq + 2 * w.Hkv) * hd;
+  const LlmWs L = llm_ws_layout(w, M, R, S, attn_splits);
+  if (workspace_bytes < L.total) return BD_ERR_WORKSPACE;
+  BD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  auto bfp = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
+  __nv_bfloat16 *a = bfp(L.a), *qkv = bfp(L.qkv), *q = bfp(L.q), *o = bfp(L.o), *g = bfp(L.g);
+  void* aws = base + L.attn;
+  const size_t aws_bytes = L.gemm - L.attn;
+  void* gws = base + L.gemm;
+  const size_t gws_bytes = L.total - L.gemm;
+  auto bf = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+
+  auto norm_to_bf16 = [&](const void* nw) {
+    if (stream_f32)
+      return launch_k(rmsnorm_kernel<true, false>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden, bf(nw),
+                      (void*)a, D, w.eps, (const float*)nullptr, 1);
+    return launch_k(rmsnorm_kernel<false, false>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden, bf(nw), (void*)a,
+                    D, w.eps, (const float*)nullptr, 1);
+  };
+
+  for (int li = 0; li < w.n_layers; ++li) {
+    const bd_llm_layer_t& lw = w.layers[li];
+    __nv_bfloat16* kpool = reinterpret_cast<__nv_bfloat16*>(kv_pool) + static_cast<long long>(li) * kv_layer_stride;
+    __nv_bfloat16* vpool = kpool + kv_v_offset;
+    BD_TRY(norm_to_bf16(lw.ln1_w));
+    {
+      GemmEpi e;
+      e.out = qkv;
+      e.ld_out = qkv_n;
+      BD_TRY(gemm_bf16(a, D, lw.wqkv, D, M, qkv_n, D, e, gws, gws_bytes, 0, 0, pdl, st));
+    }
+    {
+      const long long warps = static_cast<long long>(M) * (w.Hq + 2 * w.Hkv);
+      const unsigned grid = static_cast<unsigned>((warps * 32 + 255) / 256);
+      int rc;
+      if (hd == 128) {
+        rc = stream_f32 ? launch_k(qk_norm_rope_append_kernel<128, true>, dim3(grid), dim3(256), 0, st, pdl,
+                                   (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
+                                   (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq,
+                                   w.Hkv, w.eps, M)
+                        : launch_k(qk_norm_rope_append_kernel<128, false>, dim3(grid), dim3(256), 0, st, pdl,
+                                   (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
+                                   (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq,
+                                   w.Hkv, w.eps, M);
+      } else {
+        rc = stream_f32 ? launch_k(qk_norm_rope_append_kernel<64, true>, dim3(grid), dim3(256), 0, st, pdl,
+                                   (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
+                                   (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq,
+                                   w.Hkv, w.eps, M)
+                        : launch_k(qk_norm_rope_append_kernel<64, false>, dim3(grid), dim3(256), 0, st, pdl,
+                                   (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
+                                   (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq,
+                                   w.Hkv, w.eps, M);
+      }
+      BD_TRY(rc);
+    }
+    // keys visible to block b: seq_lens[b] (past) + S (this block), read on the device by the attention kernel
+    BD_TRY(attn_run_llm(q, kpool, vpool, page_table, max_pages, seq_lens, sk_bound, o, R, S, w.Hq, w.Hkv, hd, causal,
+                        attn_splits, aws, aws_bytes, pdl, st));
+    {
+      GemmEpi e;
+      e.res = hidden;
+      e.ld_res = D;
+      e.res_f32 = stream_f32;
+      e.out = hidden;
+      e.ld_out = D;
+      e.out_f32 = stream_f32;
+      BD_TRY(gemm_bf16(o, w.Hq * hd, lw.wo, w.Hq * hd, M, D, w.Hq * hd, e, gws, gws_bytes, 0, 0, pdl, st));
+    }
+    BD_TRY(norm_to_bf16(lw.ln2_w));
+    {
+      GemmEpi e;
+      e.swiglu = 1;
+      e.out = g;
+      e.ld_out = w.I;
+      BD_TRY(gemm_bf16(a, D, lw.w_gate_up, D, M, 2 * w.I, D, e, gws, gws_bytes, 0, 0, pdl, st));
+    }
+    {
+      GemmEpi e;
+      e.res = hidden;
+      e.ld_res = D;
+      e.res_f32 = stream_f32;
+      e.out = hidden;
+      e.ld_out = D;
+      e.out_f32 = stream_f32;
+      BD_TRY(gemm_bf16(g, w.I, lw.w_down, w.I, M, D, w.I, e, gws, gws_bytes, 0, 0, pdl, st));
+    }
+  }
+  if (stream_f32)
+    BD_TRY(launch_k(rmsnorm_kernel<true, true>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden,
+                    bf(w.final_norm_w), out, D, w.eps, out_add, out_add_mod > 0 ? out_add_mod : 1));
+  else
+    BD_TRY(launch_k(rmsnorm_kernel<false, false>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden,
+                    bf(w.final_norm_w), out, D, w.eps, (const float*)nullptr, 1));
+  BD_TRY(launch_k(bump_seq_lens_kernel, dim3(1), dim3(256), 0, st, pdl, seq_lens, R, S));
+  return BD_OK;
+}
+
+}  // extern "C"

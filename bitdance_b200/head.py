@@ -1,0 +1,199 @@
+"""Host side of the binary-diffusion vision head: weight prepack + ``bd_head_sample`` launch.
+
+Mirrors ``DiffHead.sample`` (modeling/vision_head/flow_head_parallel_x.py:107-120): the only torch work left on the
+path is drawing the noise with the SAME call sequence as the reference sampler (one ``randn`` for x0, then one per
+stochastic step; sampling_x.py:60,40) so that a seeded run consumes the CUDA Philox stream identically.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._lib import check, ptr, stream_ptr
+
+MAX_BLOCKS = 16
+
+
+class HeadBlock(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "norm1_w", "norm1_b", "norm2_w", "norm2_b",
+        "wqkv_w", "wqkv_b", "wo_w", "wo_b", "w1_w", "w1_b", "w2_w", "w2_b")]
+
+
+class HeadWeights(C.Structure):
+    _fields_ = (
+        [(n, C.c_int) for n in ("D", "Dz", "C", "hidden", "n_blocks", "n_ada", "head_dim", "use_swiglu", "out_sigmoid")]
+        + [(n, C.c_void_p) for n in ("input_proj_w", "input_proj_b", "time0_w", "time0_b", "time2_w", "time2_b",
+                                     "cond_w", "cond_b", "ada_w", "ada_b", "final_w", "final_b")]
+        + [("blocks", HeadBlock * MAX_BLOCKS)]
+    )
+
+
+def head_spec(ch_target, ch_cond, ch_latent, depth_latent, depth_adanln, use_swiglu=True, prefix="net."):
+    """State-dict spec of the reference DiffHead (names as in flow_head_parallel_x.py:254-300)."""
+    D, hid = ch_latent, int(ch_latent * 1.5)
+    s = {}
+
+    def lin(name, o, i):
+        s[prefix + name + ".weight"] = (o, i)
+        s[prefix + name + ".bias"] = (o,)
+
+    lin("time_embed.mlp.0", D, 256)
+    lin("time_embed.mlp.2", D, D)
+    lin("cond_embed", D, ch_cond)
+    lin("input_proj", D, ch_target)
+    for i in range(depth_latent):
+        b = f"res_blocks.{i}."
+        s[prefix + b + "norm1.weight"] = (D,)
+        s[prefix + b + "norm1.bias"] = (D,)
+        lin(b + "attn.wqkv", 3 * D, D)
+        lin(b + "attn.wo", D, D)
+        s[prefix + b + "norm2.weight"] = (D,)
+        s[prefix + b + "norm2.bias"] = (D,)
+        if use_swiglu:
+            lin(b + "w1", 2 * hid, D)
+            lin(b + "w2", D, hid)
+        else:
+            lin(b + "mlp.0", hid, D)
+            lin(b + "mlp.2", D, hid)
+    for i in range(depth_adanln):
+        lin(f"ada_ln_blocks.{i}", 6 * D, D)
+    lin("final_layer.ada_ln_modulation", 2 * D, D)
+    lin("final_layer.linear", ch_target, D)
+    return s
+
+
+def sampler_schedule(num_sampling_steps: int, time_shift: float = 1.0, last_step_size: float = 0.05, device="cpu"):
+    """Per-evaluation fp32 scalars [S+1, 8] = {t, dt, clamp(1-t,.05), var, 1-t, sqrt(2(1-t)dt), 0, 0}, produced with
+    the same torch fp32 tensor ops (and on the same device) as sampling_x.py:62-68,82,6-14,39 — t is the running sum
+    of dt, not linspace[i]."""
+    S = num_sampling_steps
+    t_all = torch.linspace(0, 1 - last_step_size, S + 1, device=device, dtype=torch.float32)
+    t_all = (1 / time_shift) / ((1 / time_shift) + (1 / t_all - 1) ** 1.0)
+    dt = t_all[1:] - t_all[:-1]
+    t = torch.tensor(0.0, device=device, dtype=torch.float32)
+    rows = torch.zeros(S + 1, 8, dtype=torch.float32, device=device)
+    for i in range(S):
+        sigma = 1 - t
+        var = sigma ** 2 - (t / 1) * (-1) * sigma
+        rows[i, 0] = t
+        rows[i, 1] = dt[i]
+        rows[i, 2] = (1 - t).clamp_min(0.05)
+        rows[i, 3] = var
+        rows[i, 4] = 1 - t
+        rows[i, 5] = (2.0 * (1.0 - t) * dt[i]) ** 0.5
+        t = t + dt[i]
+    tl = torch.full((), 1 - last_step_size, device=device, dtype=torch.float32)
+    rows[S, 0] = tl
+    rows[S, 1] = last_step_size
+    rows[S, 2] = (1 - tl).clamp_min(0.05)
+    rows[S, 3] = 1.0
+    rows[S, 4] = 1 - tl
+    return rows.cpu().contiguous()
+
+
+class HeadRunner:
+    """Prepacked weights + workspace for one DiffHead on one device."""
+
+    def __init__(self, state_dict: dict, *, ch_target, ch_cond, ch_latent, depth_latent, depth_adanln, use_swiglu,
+                 head_dim=128, out_sigmoid=True, time_shift=1.0, device="cuda", prefix="net."):
+        assert depth_latent <= MAX_BLOCKS
+        self.device = torch.device(device)
+        self.cfg = dict(C=ch_target, Dz=ch_cond, D=ch_latent, n_blocks=depth_latent, n_ada=depth_adanln)
+        self.time_shift = time_shift
+        self.hidden = int(ch_latent * 1.5)
+        self._keep = []  # prepacked tensors (owned here; C side sees raw pointers)
+        dev = self.device
+
+        def bf(name):
+            t = state_dict[prefix + name].detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+            self._keep.append(t)
+            return t
+
+        def f32(name):
+            t = state_dict[prefix + name].detach().to(device=dev, dtype=torch.float32).contiguous()
+            self._keep.append(t)
+            return t
+
+        w = HeadWeights()
+        w.D, w.Dz, w.C, w.hidden = ch_latent, ch_cond, ch_target, self.hidden
+        w.n_blocks, w.n_ada, w.head_dim = depth_latent, depth_adanln, head_dim
+        w.use_swiglu, w.out_sigmoid = int(use_swiglu), int(out_sigmoid)
+        for field, name in (("input_proj", "input_proj"), ("time0", "time_embed.mlp.0"), ("time2", "time_embed.mlp.2"),
+                            ("cond", "cond_embed"), ("final", "final_layer.linear")):
+            setattr(w, field + "_w", bf(name + ".weight").data_ptr())
+            setattr(w, field + "_b", bf(name + ".bias").data_ptr())
+        ada_names = [f"ada_ln_blocks.{i}" for i in range(depth_adanln)] + ["final_layer.ada_ln_modulation"]
+        ada_w = torch.cat([bf(n + ".weight") for n in ada_names], dim=0).contiguous()
+        ada_b = torch.cat([bf(n + ".bias") for n in ada_names], dim=0).contiguous()
+        self._keep += [ada_w, ada_b]
+        w.ada_w, w.ada_b = ada_w.data_ptr(), ada_b.data_ptr()
+        for i in range(depth_latent):
+            b = f"res_blocks.{i}."
+            blk = w.blocks[i]
+            blk.norm1_w, blk.norm1_b = f32(b + "norm1.weight").data_ptr(), f32(b + "norm1.bias").data_ptr()
+            blk.norm2_w, blk.norm2_b = f32(b + "norm2.weight").data_ptr(), f32(b + "norm2.bias").data_ptr()
+            blk.wqkv_w, blk.wqkv_b = bf(b + "attn.wqkv.weight").data_ptr(), bf(b + "attn.wqkv.bias").data_ptr()
+            blk.wo_w, blk.wo_b = bf(b + "attn.wo.weight").data_ptr(), bf(b + "attn.wo.bias").data_ptr()
+            if use_swiglu:
+                w1, b1 = bf(b + "w1.weight"), bf(b + "w1.bias")
+                wi, bi = ops.interleave16(w1[: self.hidden], w1[self.hidden:], b1[: self.hidden], b1[self.hidden:])
+                self._keep += [wi, bi]
+                self._keep = [t for t in self._keep if t is not w1]  # un-interleaved copy not needed
+                blk.w1_w, blk.w1_b = wi.data_ptr(), bi.data_ptr()
+                blk.w2_w, blk.w2_b = bf(b + "w2.weight").data_ptr(), bf(b + "w2.bias").data_ptr()
+            else:
+                blk.w1_w, blk.w1_b = bf(b + "mlp.0.weight").data_ptr(), bf(b + "mlp.0.bias").data_ptr()
+                blk.w2_w, blk.w2_b = bf(b + "mlp.2.weight").data_ptr(), bf(b + "mlp.2.bias").data_ptr()
+        torch.cuda.synchronize(dev)
+        self.w = w
+        self._ws = None
+        self._sched = {}
+
+    def schedule(self, S: int) -> torch.Tensor:
+        if S not in self._sched:
+            self._sched[S] = sampler_schedule(S, self.time_shift, device=self.device)
+        return self._sched[S]
+
+    def _workspace(self, B, pn, mult, S):
+        lib = _lib.load()
+        lib.bd_head_workspace_bytes.restype = C.c_size_t
+        need = lib.bd_head_workspace_bytes(C.byref(self.w), B, pn, mult, S)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def draw_noise(self, B, pn, S):
+        """Same generator consumption as sampling_x.py: randn(x_shape) then S x randn_like(x)."""
+        Cc = self.cfg["C"]
+        noise = torch.empty((S + 1, B, pn, Cc), dtype=torch.float32, device=self.device)
+        for i in range(S + 1):
+            noise[i].normal_()
+        return noise
+
+    def sample(self, z: torch.Tensor, cfg: float, num_sampling_steps: int, noise: torch.Tensor | None = None,
+               trace: bool = False, pdl: bool = True):
+        """z: [R, pn, Dz] fp32 (cond rows then uncond rows when cfg > 1). Returns x [B, pn, C] fp32 (+ trace)."""
+        lib = _lib.load()
+        assert z.is_cuda and z.dim() == 3
+        mult = 2 if cfg > 1.0 else 1
+        R, pn, Dz = z.shape
+        assert R % mult == 0 and Dz == self.cfg["Dz"]
+        B = R // mult
+        S = num_sampling_steps
+        Cc = self.cfg["C"]
+        if noise is None:
+            noise = self.draw_noise(B, pn, S)
+        assert noise.shape == (S + 1, B, pn, Cc) and noise.dtype == torch.float32 and noise.is_contiguous()
+        zc = z.to(torch.float32).contiguous()
+        out = torch.empty((B, pn, Cc), dtype=torch.float32, device=self.device)
+        tr = torch.empty((S + 1, R * pn, Cc), dtype=torch.float32, device=self.device) if trace else None
+        ws = self._workspace(B, pn, mult, S)
+        sched = self.schedule(S)
+        st = lib.bd_head_sample(C.byref(self.w), ptr(zc), ptr(noise), C.c_void_p(sched.data_ptr()), B, pn, mult,
+                                C.c_float(cfg), S, ptr(out), ptr(tr), ptr(ws), C.c_size_t(ws.numel()),
+                                1 if pdl else 0, stream_ptr())
+        check(st, "bd_head_sample")
+        return (out, tr) if trace else out

@@ -45,6 +45,7 @@ def gemm(
     swiglu: bool = False,
     gate: torch.Tensor | None = None,
     res: torch.Tensor | None = None,
+    res_row_mod: int = 0,
     out: torch.Tensor | None = None,
     out_dtype: torch.dtype = torch.bfloat16,
     bn: int = 0,
@@ -77,13 +78,15 @@ def gemm(
     epi.ld_res = res.stride(0) if res is not None else 0
     epi.res_f32 = 0
     if res is not None:
-        assert res.shape == (M, N) and res.stride(1) == 1 and res.dtype in (torch.bfloat16, torch.float32)
+        assert res.shape == ((res_row_mod or M), N) and res.stride(1) == 1
+        assert res.dtype in (torch.bfloat16, torch.float32)
         epi.res_f32 = 1 if res.dtype == torch.float32 else 0
     epi.out = out.data_ptr()
     epi.ld_out = out.stride(0)
     epi.act = ACT[act]
     epi.swiglu = 1 if swiglu else 0
     epi.out_f32 = 1 if out.dtype == torch.float32 else 0
+    epi.res_row_mod = res_row_mod
     ws_bytes = lib.bd_gemm_workspace_bytes(M, N, K, bn, splits)
     ws = (workspace or default_workspace(a.device)).get(ws_bytes)
     st = lib.bd_gemm_bf16(
@@ -147,4 +150,42 @@ def unpack_tokens(packed: torch.Tensor, C_bits: int, dtype=torch.float32):
     out = torch.empty((*packed.shape[:-1], C_bits), dtype=dtype, device=packed.device)
     check(lib.bd_unpack_tokens(ptr(packed), C.c_longlong(rows), C_bits, ptr(out), 1 if dtype == torch.float32 else 0,
                                stream_ptr()), "bd_unpack_tokens")
+    return out
+
+
+def attention(q, k, v, *, causal=False, scale=None, page_table=None, sk=None, splits=0, out=None, pdl=False,
+              workspace: Workspace | None = None):
+    """Flash-style attention (see ``bd_attention_bf16``).
+
+    strided: q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D] (any strides with contiguous last dim);
+    paged:   k/v pools [n_pages, Hkv, 64, D] contiguous, page_table int32 [B, max_pages], ``sk`` = valid keys.
+    Returns [B,Sq,Hq,D] bf16."""
+    lib = _lib.load()
+    require_cuda(q, k, v)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16 and q.stride(-1) == 1
+    B, Sq, Hq, D = q.shape
+    if page_table is None:
+        assert k.stride(-1) == 1 and v.stride() == k.stride()
+        Sk, Hkv = k.shape[1], k.shape[2]
+        ksb, kss, ksh = k.stride(0), k.stride(1), k.stride(2)
+        pt, max_pages = None, 0
+    else:
+        assert k.is_contiguous() and v.is_contiguous() and k.shape[2] == 64 and page_table.dtype == torch.int32
+        Sk, Hkv = int(sk), k.shape[1]
+        ksb = kss = ksh = 0
+        pt, max_pages = page_table.contiguous(), page_table.shape[1]
+    if out is None:
+        out = torch.empty((B, Sq, Hq, D), dtype=torch.bfloat16, device=q.device)
+    if scale is None:
+        scale = D ** -0.5
+    lib.bd_attention_workspace_bytes.restype = C.c_size_t
+    need = lib.bd_attention_workspace_bytes(B, Hq, Sq, Sk, D, splits)
+    ws = (workspace or default_workspace(q.device)).get(need)
+    st = lib.bd_attention_bf16(
+        ptr(q), C.c_int64(q.stride(0)), C.c_int64(q.stride(1)), C.c_int64(q.stride(2)), ptr(k), ptr(v),
+        C.c_int64(ksb), C.c_int64(kss), C.c_int64(ksh), ptr(pt), max_pages, ptr(out), C.c_int64(out.stride(0)),
+        C.c_int64(out.stride(1)), C.c_int64(out.stride(2)), B, Sq, Sk, Hq, Hkv, D, 1 if causal else 0,
+        C.c_float(scale), splits, ptr(ws), C.c_size_t(ws.numel() if ws is not None else 0), 1 if pdl else 0,
+        stream_ptr())
+    check(st, "bd_attention_bf16")
     return out

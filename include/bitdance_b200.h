@@ -73,6 +73,7 @@ typedef struct {
   int swiglu;  /* 1: W rows are interleave16(gate, up) (bd_interleave16); out has N/2 columns */
   int res_f32;
   int out_f32;
+  int res_row_mod; /* > 0: res is a [res_row_mod, N] table, row m uses res[m % res_row_mod] (pos-embed broadcast) */
 } bd_gemm_epilogue_t;
 
 /* out = epilogue(A[M,K] · W[N,K]^T): F.linear under autocast(bf16) (+ the elementwise ops that follow it in
@@ -91,6 +92,109 @@ size_t bd_gemm_workspace_bytes(int M, int N, int K, int bn, int splits);
  * bias_* (bf16 [F]) / bias_out (bf16 [2F]) may be NULL. */
 int bd_interleave16(const void* gate, const void* up, void* out, int F, int K, const void* bias_gate,
                     const void* bias_up, void* bias_out, bd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention (diffusion-head MHA and Qwen3 GQA over a paged KV cache)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* softmax(Q K^T * scale [+ causal mask]) V with fp32 scores/softmax, bf16 P and output (flash-attention semantics):
+ * Attention.forward flow_head_parallel_x.py:192-220 and Qwen3Attention (transformers, called from
+ * modeling/t2i_pipeline.py:199-266; an all-ones mask = causal 0). Strides in ELEMENTS: (b, s, h, d) at
+ * base + b*sb + s*ss + h*sh + d. KV either strided (page_table NULL) or paged: page_table int32 [B, max_pages],
+ * pools k/v laid out [page][Hkv][64 tokens][head_dim]. causal: key j visible to query i iff j <= i + (Sk - Sq).
+ * splits: 0 = auto split of the KV range (deterministic fixed-order combine), needs bd_attention_workspace_bytes. */
+int bd_attention_bf16(const void* q, int64_t q_sb, int64_t q_ss, int64_t q_sh, const void* k, const void* v,
+                      int64_t k_sb, int64_t k_ss, int64_t k_sh, const int32_t* page_table, int max_pages, void* out,
+                      int64_t o_sb, int64_t o_ss, int64_t o_sh, int B, int Sq, int Sk, int Hq, int Hkv, int head_dim,
+                      int causal, float scale, int splits, void* workspace, size_t workspace_bytes, int flags,
+                      bd_stream_t stream);
+size_t bd_attention_workspace_bytes(int B, int Hq, int Sq, int Sk, int head_dim, int splits);
+
+/* ------------------------------------------------------------------------------------------------
+ * Binary-diffusion vision head: DiffHead.sample in one call
+ * ---------------------------------------------------------------------------------------------- */
+
+#define BD_HEAD_MAX_BLOCKS 16
+
+typedef struct {
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b; /* fp32 [D] */
+  /* bf16 nn.Linear weights [out, in] and bf16 biases. w1: interleave16(h1 rows, h2 rows) when use_swiglu
+   * (w1.weight.chunk(2) = rows [0,hidden) and [hidden,2*hidden)), else mlp.0; w2: w2 / mlp.2. */
+  const void *wqkv_w, *wqkv_b, *wo_w, *wo_b, *w1_w, *w1_b, *w2_w, *w2_b;
+} bd_head_block_t;
+
+typedef struct {
+  int D;        /* ch_latent */
+  int Dz;       /* ch_cond */
+  int C;        /* ch_target (bits per token) */
+  int hidden;   /* int(1.5 * D) */
+  int n_blocks; /* depth_latent */
+  int n_ada;    /* depth_adanln */
+  int head_dim; /* 128 (modeling/) or 64 (imagenet_gen/) */
+  int use_swiglu;
+  int out_sigmoid; /* 1: 2*sigmoid(.)-1 (flow_head_parallel_x.py:341-342); 0: imagenet_gen diff_head_parallel.py:310 */
+  const void *input_proj_w, *input_proj_b;
+  const void *time0_w, *time0_b, *time2_w, *time2_b; /* time_embed.mlp.0 / .2 */
+  const void *cond_w, *cond_b;
+  const void *ada_w, *ada_b;     /* rows: ada_ln_blocks[0] (6D) | ... | ada_ln_blocks[n_ada-1] | final_layer.ada_ln_modulation (2D) */
+  const void *final_w, *final_b; /* final_layer.linear [C, D] */
+  bd_head_block_t blocks[BD_HEAD_MAX_BLOCKS];
+} bd_head_weights_t;
+
+/* DiffHead.sample(z, cfg, num_sampling_steps) = euler_maruyama (modeling/vision_head/sampling_x.py:44-97) over
+ * TransEncoder.forward (flow_head_parallel_x.py:325-342).
+ *   cond       fp32 [B*cfg_mult*pn, Dz]: z, conditional rows first then unconditional rows (t2i_pipeline.py:244)
+ *   noise      fp32 [(S+1), B*pn, C]: noise[0] = the torch.randn of :60, noise[1+i] = the randn_like of step i (:40)
+ *   sched_host HOST fp32 [(S+1), 8]: per evaluation {t, dt, clamp(1-t,0.05), var, 1-t, sqrt(2(1-t)dt), 0, 0} computed
+ *              with the reference's fp32 scalar arithmetic (t is the running sum of dt); row S: t=0.95.., dt=last step
+ *   x_out      fp32 [B*pn, C] final continuous sample (the reference returns cat([x]*cfg_mult); sign() is the caller's)
+ *   trace      optional fp32 [(S+1), B*cfg_mult*pn, C]: the network output of every evaluation (tests)
+ * Rounding: autocast(bf16) policy (oracle/head.py docstring); sampler state fp32 with unfused mul/add. */
+int bd_head_sample(const bd_head_weights_t* w, const float* cond, const float* noise, const float* sched_host, int B,
+                   int pn, int cfg_mult, float cfg, int S, float* x_out, float* trace, void* workspace,
+                   size_t workspace_bytes, int flags, bd_stream_t stream);
+size_t bd_head_workspace_bytes(const bd_head_weights_t* w, int B, int pn, int cfg_mult, int S);
+
+/* ------------------------------------------------------------------------------------------------
+ * Qwen3 decoder stack with a paged KV cache
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  const void *ln1_w, *ln2_w;       /* bf16 [D]: input_layernorm / post_attention_layernorm */
+  const void *q_norm_w, *k_norm_w; /* bf16 [head_dim] */
+  const void* wqkv;                /* bf16 [(Hq + 2 Hkv) * head_dim, D]: rows q_proj | k_proj | v_proj */
+  const void* wo;                  /* bf16 [D, Hq * head_dim] */
+  const void* w_gate_up;           /* bf16 [2 I, D]: bd_interleave16(gate_proj, up_proj) */
+  const void* w_down;              /* bf16 [D, I] */
+} bd_llm_layer_t;
+
+typedef struct {
+  int D, I, n_layers, Hq, Hkv, head_dim;
+  float eps;
+  const void* final_norm_w;     /* bf16 [D] */
+  const bd_llm_layer_t* layers; /* HOST array [n_layers] */
+} bd_llm_weights_t;
+
+/* Qwen3Model.forward(inputs_embeds, past_key_values, attention_mask) as the reference calls it at
+ * modeling/t2i_pipeline.py:199,211,224,229 (prefill) and :261,266 (AR block) — third-party transformers==4.57.0.
+ *   hidden      [R*S, D] residual stream, fp32 (stream_f32=1: AR blocks, inputs_embeds = bf16 + fp32 pos-embed) or bf16
+ *               (prefill); holds inputs_embeds on entry and is overwritten.
+ *   seq_lens    DEVICE int32 [R] (R <= 256): tokens already cached per sequence; position of token (b,s) is
+ *               seq_lens[b]+s; incremented by S on the device at the end (graph-replay safe). sk_bound = host upper
+ *               bound of seq_lens[b]+S (planning only).
+ *   causal      1: first prefill call; 0: all-ones mask = the S new tokens see the whole cache and each other
+ *   kv_pool     bf16; layer l keys at kv_pool + l*kv_layer_stride, values at + kv_v_offset (elements); each pool is
+ *               [n_pages][Hkv][64][head_dim]; page_table DEVICE int32 [R, max_pages]
+ *   rope_cos/sin fp32 [>= sk_bound, head_dim] tables (cos/sin of cat(freqs, freqs), Qwen3RotaryEmbedding)
+ *   out         final-RMSNorm output [R*S, D] in the stream dtype; out_add (fp32 [out_add_mod, D], stream_f32 only)
+ *               is added row-wise with m % out_add_mod: h_fused = last_hidden_state + pos_embed (t2i_pipeline.py:245)
+ * Rounding policy: oracle/llm.py. */
+int bd_llm_forward(const bd_llm_weights_t* w, void* hidden, int stream_f32, int R, int S, int* seq_lens, int sk_bound,
+                   int causal, void* kv_pool, int64_t kv_layer_stride, int64_t kv_v_offset, const int32_t* page_table,
+                   int max_pages, const float* rope_cos, const float* rope_sin, void* out, const float* out_add,
+                   int out_add_mod, int attn_splits, void* workspace, size_t workspace_bytes, int flags,
+                   bd_stream_t stream);
+size_t bd_llm_workspace_bytes(const bd_llm_weights_t* w, int R, int S, int attn_splits);
 
 #ifdef __cplusplus
 }
