@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on its config: 1024px images/sec, BitDance-14B-64x (random-init, synthetic prompt).
+
+One "step" = one pass of the hot path over one batch: prefill -> 64 AR steps (each = 51 diffusion-head evaluations +
+sign + projector + one Qwen3-14B block pass) -> tokenizer decode, for ``--bs`` images. See DESIGN.md §Measurement.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores (oracle port)
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "BitDance-14B-64x"
+METRIC = "1024px images/sec (14B-64x)"
+P_LLM, P_HEAD, P_COND, P_PROJ = 13.2125e9, 1.7585e9, 26.2e6, 26.4e6
+KV_BYTES_PER_TOKEN = 163840
+
+
+def algorithmic_bytes_per_ar_step(R: int, S: int, avg_ctx: float) -> float:
+    """weights streamed once per AR step (cond+uncond batched, cond_embed hoisted) + KV reads."""
+    return 2 * P_LLM + (S + 1) * 2 * (P_HEAD - P_COND) + 2 * (P_COND + P_PROJ) + R * avg_ctx * KV_BYTES_PER_TOKEN
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores, bounded sample, extrapolated
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(S: int, threads: int):
+    """Times, at the 14B-64x dimensions (M = 128 rows), ONE diffusion-head evaluation (all 6 blocks sharing one
+    block's random weights to bound RAM) and ONE Qwen3 decoder layer over a 2100-token cache, fp32 math via the oracle
+    port (oracle/head.py, oracle/llm.py), then extrapolates an image: 64 x (51 head evals + 40 layers) (prefill and
+    tokenizer decode excluded: < 2 % of the work). Returns (images_per_sec, seconds_measured, description)."""
+    import torch
+    from oracle import head as oh, llm as ol
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    D, hid, C, pn, R = 5120, 7680, 32, 64, 2
+
+    def lin(o, i):
+        return torch.randn(o, i) * 0.02, torch.zeros(o)
+
+    sd = {}
+    for name, (o, i) in {"net.time_embed.mlp.0": (D, 256), "net.time_embed.mlp.2": (D, D), "net.cond_embed": (D, D),
+                         "net.input_proj": (D, C), "net.final_layer.ada_ln_modulation": (2 * D, D),
+                         "net.final_layer.linear": (C, D)}.items():
+        sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
+    blk = {"attn.wqkv": (3 * D, D), "attn.wo": (D, D), "w1": (2 * hid, D), "w2": (D, hid)}
+    shared = {k: lin(*v) for k, v in blk.items()}
+    ada = lin(6 * D, D)
+    for b in range(6):
+        for k, (w, bias) in shared.items():
+            sd[f"net.res_blocks.{b}.{k}.weight"], sd[f"net.res_blocks.{b}.{k}.bias"] = w, bias
+        for n in ("norm1", "norm2"):
+            sd[f"net.res_blocks.{b}.{n}.weight"], sd[f"net.res_blocks.{b}.{n}.bias"] = torch.ones(D), torch.zeros(D)
+    for a in range(2):
+        sd[f"net.ada_ln_blocks.{a}.weight"], sd[f"net.ada_ln_blocks.{a}.bias"] = ada
+    x, t, c = torch.randn(R, pn, C), torch.full((R,), 0.3), torch.randn(R, pn, D)
+    cfg = dict(num_attention_heads=40, num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6,
+               num_hidden_layers=1)
+    sdl = {"model.layers.0.input_layernorm.weight": torch.ones(D), "model.layers.0.post_attention_layernorm.weight": torch.ones(D),
+           "model.layers.0.self_attn.q_norm.weight": torch.ones(128), "model.layers.0.self_attn.k_norm.weight": torch.ones(128),
+           "model.norm.weight": torch.ones(D)}
+    for n, (o, i) in {"self_attn.q_proj": (5120, D), "self_attn.k_proj": (1024, D), "self_attn.v_proj": (1024, D),
+                      "self_attn.o_proj": (D, 5120), "mlp.gate_proj": (17408, D), "mlp.up_proj": (17408, D),
+                      "mlp.down_proj": (D, 17408)}.items():
+        sdl[f"model.layers.0.{n}.weight"] = torch.randn(o, i) * 0.02
+    ctx = 2100
+    with torch.no_grad():
+        oh.head_forward(sd, x, t, c)  # warm-up (thread pool, allocator)
+        t0 = time.perf_counter()
+        oh.head_forward(sd, x, t, c)
+        t_head = time.perf_counter() - t0
+        cache = [[torch.randn(R, 8, ctx, 128), torch.randn(R, 8, ctx, 128)]]
+        xin = torch.randn(R, pn, D)
+        t0 = time.perf_counter()
+        ol.decoder_forward(sdl, cfg, xin, cache, causal=False)
+        t_layer = time.perf_counter() - t0
+    sec_per_image = 64 * ((S + 1) * t_head + 40 * t_layer)
+    desc = (f"oracle port fp32, {threads} threads: 1 head evaluation ({t_head:.2f} s, M=128, 1.76 B params) + 1 Qwen3-14B "
+            f"layer over a {ctx}-token cache ({t_layer:.2f} s), extrapolated to 64 x ({S + 1} evals + 40 layers)")
+    return 1.0 / sec_per_image, t_head + t_layer, desc
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    desc = ""
+    for i in range(args.warmup + args.steps):
+        v, secs, desc = cpu_reference_sample(args.sampling_steps, threads)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{MODEL} random-init, 1024x1024, 64 AR steps, bs=1, CFG 7.5, S={args.sampling_steps}",
+                       "extrapolated": True},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="bitdance_b200", choices=["bitdance_b200", "reference"])
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--bs", type=int, default=1)
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--sampling-steps", type=int, default=50)
+    ap.add_argument("--guidance", type=float, default=7.5)
+    ap.add_argument("--ar-steps", type=int, default=None, help="debug only: truncate the AR loop (invalidates the metric)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from bitdance_b200 import _lib
+    from bitdance_b200.synthetic import MODELS, build_synthetic_engine
+
+    lib = _lib.load()
+    lib.bd_launch_count.restype = __import__("ctypes").c_ulonglong
+    _lib.check(lib.bd_device_check(), "bd_device_check")
+    eng, embed = build_synthetic_engine(args.model, dev, seed=rank)
+    m = MODELS[args.model]
+    pn, vps = m["parallel_num"], eng.vae_patch_size
+    h, w = args.height // vps, args.width // vps
+    B, S = args.bs, args.sampling_steps
+    R = 2 * B if args.guidance > 1.0 else B
+    # synthetic prompt: 64 cond ids, 3 uncond ids, fixed special ids
+    g = torch.Generator().manual_seed(1 + rank)
+    cond_ids = torch.randint(0, 151000, (64,), generator=g)
+    uncond_ids = torch.randint(0, 151000, (3,), generator=g)
+    start_ids = torch.tensor([151700, 151701 + h % 100, 151701 + w % 100] + [151810 + i for i in range(1, pn)])
+    ids_host = torch.cat([cond_ids, uncond_ids, start_ids]).pin_memory()
+    img_host = torch.empty((B, args.height, args.width, 3), dtype=torch.uint8).pin_memory()
+
+    def gen_resident(ids_dev):
+        ce, ue, se = embed[ids_dev[:64]], embed[ids_dev[64:67]], embed[ids_dev[67:]]
+        tokens, packed = eng.gen_tokens(ce, ue, se, h=h, w=w, num_images=B, guidance_scale=args.guidance,
+                                        num_sampling_steps=S, num_steps=args.ar_steps)
+        if args.ar_steps is not None:
+            return None
+        return eng.decode(tokens, h, w)
+
+    def gen_e2e():
+        """The public call with HOST buffers: token ids H2D, uint8 pixels D2H (generate(), t2i_pipeline.py:110-155)."""
+        ids_dev = ids_host.to(dev, non_blocking=True)
+        img = gen_resident(ids_dev)
+        if img is None:
+            return
+        u8 = torch.clamp(127.5 * img + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+        img_host.copy_(u8, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ids_dev = ids_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        gen_resident(ids_dev)
+    barrier()
+    launches0 = lib.bd_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            gen_resident(ids_dev)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.bd_launch_count() - launches0
+    # per-phase split of the last configuration (one extra, untimed-for-the-metric pass)
+    eng.gen_tokens(embed[ids_dev[:64]], embed[ids_dev[64:67]], embed[ids_dev[67:]], h=h, w=w, num_images=B,
+                   guidance_scale=args.guidance, num_sampling_steps=S, num_steps=args.ar_steps, timers=True)
+    phases = dict(eng.timings)
+    # e2e through host buffers
+    gen_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        gen_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    n_img = world * B * args.steps
+    value = n_img / (ms / 1e3)
+    e2e_value = n_img / (ms_e2e / 1e3)
+    ar_steps = phases.get("ar_steps", 0)
+    ms_ar = 1e3 * phases.get("ar_s", 0.0) / max(ar_steps, 1)
+    avg_ctx = 64 / 2 + 2 + pn + (h * w) / 2
+    step_bytes = algorithmic_bytes_per_ar_step(R, S, avg_ctx)
+    roof = dominant_kernel_roofline(eng, hbm_peak, peak_src)
+    roof["ar_step"] = {"algorithmic_gb": step_bytes / 1e9, "ms": ms_ar, "achieved_gbs": step_bytes / 1e9 / (ms_ar / 1e3) if ms_ar else None,
+                       "frac": (step_bytes / 1e9 / (ms_ar / 1e3)) / hbm_peak if ms_ar else None}
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.model} random-init, {args.height}x{args.width}, {(h * w) // pn} AR steps, bs={B}/GPU, "
+                               f"CFG {args.guidance}, S={S} (+1), synthetic 64-token prompt",
+                   "parallelism": f"replicas x{world} (independent images per GPU, no data-path collective)",
+                   "l2": "inputs >> L2: 33 GB of bf16 weights streamed per AR step",
+                   "ms_per_ar_step": ms_ar, "prefill_ms": 1e3 * phases.get("prefill_s", 0.0),
+                   "truncated_ar_steps": args.ar_steps},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(ids_host.numel() * 8),
+                "d2h_bytes_per_step": int(img_host.numel())},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+    }
+    if not args.no_cpu_baseline:
+        v, secs, desc = cpu_reference_sample(S, os.cpu_count() or 1)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(eng, hbm_peak, peak_src):
+    """bd_gemm_kernel<128> on the head's wqkv Linears (M=128, N=15360, K=5120; 157 MB of bf16 weights per launch, the
+    shape that dominates the step's bytes). Timed live with CUDA events on the launching stream: 6 different weight
+    matrices (944 MB >> L2) launched round-robin, so every launch streams its weights from HBM."""
+    import torch
+    from bitdance_b200 import ops
+    head = eng.head
+    D = head.cfg["D"]
+    ws = [t for t in head._keep if t.dim() == 2 and t.shape == (3 * D, D)]
+    if not ws:
+        return {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None}
+    a = torch.randn(128, D, device=ws[0].device).to(torch.bfloat16)
+    out = torch.empty(128, 3 * D, dtype=torch.bfloat16, device=a.device)
+    for w in ws:
+        ops.gemm(a, w, out=out)
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for w in ws:
+            ops.gemm(a, w, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * len(ws))
+    bytes_alg = (3 * D * D + 128 * D + 128 * 3 * D) * 2
+    ach = bytes_alg / 1e9 / (ms / 1e3)
+    return {"bound": "hbm", "kernel": "bd_gemm_kernel<128> M=128 N=%d K=%d" % (3 * D, D), "achieved": ach, "peak": hbm_peak,
+            "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "us_per_launch": ms * 1e3,
+            "algorithmic_bytes_per_launch": bytes_alg}
+
+
+if __name__ == "__main__":
+    main()

@@ -241,7 +241,7 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // Deterministic split-K reduction + epilogue: one thread per (row, 32-column chunk).
-__global__ void __launch_bounds__(256) bd_splitk_epilogue_kernel(const float* __restrict__ partial, int M, int N,
+static __global__ void __launch_bounds__(256) bd_splitk_epilogue_kernel(const float* __restrict__ partial, int M, int N,
                                                                   int splits, GemmEpi epi) {
   grid_dep_launch();
   grid_dep_wait();

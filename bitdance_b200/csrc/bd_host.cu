@@ -6,6 +6,7 @@
 namespace bd {
 
 thread_local int g_last_cuda_error = 0;
+unsigned long long g_launch_count = 0;
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -91,6 +92,7 @@ const char* bd_strerror(int status) {
 
 int bd_last_cuda_error(void) { return bd::g_last_cuda_error; }
 int bd_abi_version(void) { return 1; }
+unsigned long long bd_launch_count(void) { return bd::g_launch_count; }
 
 int bd_device_check(void) {
   int n = 0;

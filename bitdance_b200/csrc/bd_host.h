@@ -9,6 +9,7 @@
 namespace bd {
 
 extern thread_local int g_last_cuda_error;
+extern unsigned long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = static_cast<int>(e);
@@ -19,7 +20,11 @@ inline int cuda_fail(cudaError_t e) {
     cudaError_t _e = (expr);                             \
     if (_e != cudaSuccess) return ::bd::cuda_fail(_e);   \
   } while (0)
-#define BD_LAUNCH_CHECK() BD_CUDA_TRY(cudaGetLastError())
+#define BD_LAUNCH_CHECK()           \
+  do {                              \
+    ++::bd::g_launch_count;         \
+    BD_CUDA_TRY(cudaGetLastError()); \
+  } while (0)
 #define BD_REQUIRE(cond)              \
   do {                                \
     if (!(cond)) return BD_ERR_INVALID; \
@@ -74,6 +79,7 @@ struct LaunchCfg {
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    ++g_launch_count;
   }
 };
 

@@ -239,7 +239,6 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
   BD_REQUIRE(w.head_dim == 128 || w.head_dim == 64);
   BD_REQUIRE((w.D % 64) == 0 && (w.I % 64) == 0 && (w.Hq % w.Hkv) == 0);
   BD_REQUIRE(attn_splits >= 1 && sk_bound >= S && max_pages * 64 >= sk_bound);
-  BD_REQUIRE(!out_add || stream_f32);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const bool pdl = (flags & 1) != 0;
   const int M = R * S, D = w.D, hd = w.head_dim;
@@ -334,6 +333,9 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
   }
   if (stream_f32)
     BD_TRY(launch_k(rmsnorm_kernel<true, true>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden,
+                    bf(w.final_norm_w), out, D, w.eps, out_add, out_add_mod > 0 ? out_add_mod : 1));
+  else if (out_add)  // bf16 stream, fp32 output: float(bf16 norm) + pos (first h_fused after prefill, :218,245)
+    BD_TRY(launch_k(rmsnorm_kernel<false, true>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden,
                     bf(w.final_norm_w), out, D, w.eps, out_add, out_add_mod > 0 ? out_add_mod : 1));
   else
     BD_TRY(launch_k(rmsnorm_kernel<false, false>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden,

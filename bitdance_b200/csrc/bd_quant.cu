@@ -79,6 +79,49 @@ __global__ void __launch_bounds__(256) sign_tokens_kernel(const float* __restric
   if (packed) packed[w] = bits;
 }
 
+// AR-step variant: x fp32 [B*pn, C] -> tokens fp32 scattered into a [B, rows_per_image, C] grid at row offset row0
+// (out_tokens.append + torch.cat, t2i_pipeline.py:250,270), bf16 copies for `dup` sequence groups (the cond | uncond
+// rows of curr_tokens feed MLPconnector identically), and packed bits.
+__global__ void __launch_bounds__(256) sign_tokens_ex_kernel(const float* __restrict__ x, int B, int pn, int C,
+                                                             float* __restrict__ grid, long long rows_per_image,
+                                                             long long row0, __nv_bfloat16* __restrict__ tb, int dup,
+                                                             uint32_t* __restrict__ packed) {
+  const int wpr = C / 32;
+  const long long nwords = static_cast<long long>(B) * pn * wpr;
+  const long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= nwords) return;
+  const long long r = w / wpr;
+  const int cw = static_cast<int>(w % wpr);
+  const int b = static_cast<int>(r / pn), s = static_cast<int>(r % pn);
+  const float4* src = reinterpret_cast<const float4*>(x + w * 32);
+  float4* dst = grid ? reinterpret_cast<float4*>(grid + ((b * rows_per_image + row0 + s) * C + cw * 32)) : nullptr;
+  uint32_t bits = 0;
+  float sv[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 v = src[j];
+    const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sv[4 * j + i] = static_cast<float>((a[i] > 0.f) - (a[i] < 0.f));
+      bits |= (a[i] > 0.f ? 1u : 0u) << (4 * j + i);
+    }
+    if (dst) dst[j] = make_float4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
+  }
+  if (packed) packed[(b * rows_per_image + row0 + s) * wpr + cw] = bits;
+  if (tb) {
+    uint4 pk[4];
+    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p2[j] = __floats2bfloat162_rn(sv[2 * j], sv[2 * j + 1]);
+    for (int d = 0; d < dup; ++d) {
+      uint4* o = reinterpret_cast<uint4*>(tb + ((static_cast<long long>(d) * B * pn + r) * C + cw * 32));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = pk[j];
+    }
+  }
+}
+
 template <bool F32>
 __global__ void __launch_bounds__(256) unpack_tokens_kernel(const uint32_t* __restrict__ packed, long long nwords,
                                                             void* __restrict__ out) {
@@ -141,6 +184,18 @@ int bd_sign_tokens(const float* x, long long rows, int C, float* tokens, uint32_
   if (nwords == 0) return BD_OK;
   sign_tokens_kernel<<<static_cast<unsigned>((nwords + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, nwords, tokens, packed);
+  BD_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+int bd_sign_tokens_ex(const float* x, int B, int pn, int C, float* grid, long long rows_per_image, long long row0,
+                      void* tokens_bf16, int dup, uint32_t* packed, bd_stream_t stream) {
+  BD_REQUIRE(x && B > 0 && pn > 0 && C > 0 && (C % 32) == 0 && dup >= 0 && row0 >= 0 && rows_per_image >= row0 + pn);
+  BD_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(tokens_bf16) & 15) == 0);
+  const long long nwords = static_cast<long long>(B) * pn * (C / 32);
+  sign_tokens_ex_kernel<<<static_cast<unsigned>((nwords + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, B, pn, C, grid, rows_per_image, row0, static_cast<__nv_bfloat16*>(tokens_bf16), dup, packed);
   BD_LAUNCH_CHECK();
   return BD_OK;
 }

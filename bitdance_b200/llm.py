@@ -172,10 +172,11 @@ class LlmRunner:
         need = lib.bd_llm_workspace_bytes(C.byref(self.w), R, S, attn_splits)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        out = torch.empty_like(hidden)
+        out = torch.empty(hidden.shape, dtype=torch.float32 if (stream_f32 or out_add is not None) else torch.bfloat16,
+                          device=self.device)
         pool = cache.pool
         if out_add is not None:
-            assert stream_f32 and out_add.dtype == torch.float32 and out_add.is_contiguous() and out_add.shape[-1] == D
+            assert out_add.dtype == torch.float32 and out_add.is_contiguous() and out_add.shape[-1] == D
         st = lib.bd_llm_forward(
             C.byref(self.w), ptr(hidden), 1 if stream_f32 else 0, R, S, ptr(cache.seq_lens[r0:r0 + R]), sk_bound,
             1 if causal else 0, ptr(pool), C.c_int64(pool.stride(0)), C.c_int64(pool.stride(1)),

@@ -36,6 +36,7 @@ const char* bd_strerror(int status);
 int bd_last_cuda_error(void);   /* cudaError_t of the most recent BD_ERR_CUDA on this thread */
 int bd_abi_version(void);       /* bumped on any signature change */
 int bd_device_check(void);      /* BD_OK when the current device is sm_100 */
+unsigned long long bd_launch_count(void); /* kernels launched by this library since load (all threads) */
 
 /* ------------------------------------------------------------------------------------------------
  * Binary quantiser + bit packing
@@ -55,6 +56,14 @@ int bd_sign_pack_nchw(const void* h, int h_f32, int B, int C, int HW, void* quan
  * x: fp32 [rows, C] token-major. tokens: fp32 [rows, C] (may alias x; may be NULL);
  * packed: uint32 [rows, C/32], bit set iff x > 0 (may be NULL). */
 int bd_sign_tokens(const float* x, long long rows, int C, float* tokens, uint32_t* packed, bd_stream_t stream);
+
+/* AR-step form of the same op: x fp32 [B*pn, C] (the sampler output of one block). Writes (each optional):
+ *   grid        fp32 [B, rows_per_image, C] tokens at rows row0..row0+pn (out_tokens.append / torch.cat, :250,270)
+ *   tokens_bf16 bf16 [dup*B*pn, C]: the +-1/0 tokens repeated for `dup` sequence groups (cond | uncond rows of
+ *               curr_tokens, the MLPconnector input)
+ *   packed      uint32 [B, rows_per_image, C/32] bits (x > 0) at the same rows */
+int bd_sign_tokens_ex(const float* x, int B, int pn, int C, float* grid, long long rows_per_image, long long row0,
+                      void* tokens_bf16, int dup, uint32_t* packed, bd_stream_t stream);
 
 /* Inverse of the packing: packed uint32 [rows, C/32] -> +-1 in fp32 or bf16, token-major [rows, C]. */
 int bd_unpack_tokens(const uint32_t* packed, long long rows, int C, void* out, int out_f32, bd_stream_t stream);
@@ -186,8 +195,9 @@ typedef struct {
  *   kv_pool     bf16; layer l keys at kv_pool + l*kv_layer_stride, values at + kv_v_offset (elements); each pool is
  *               [n_pages][Hkv][64][head_dim]; page_table DEVICE int32 [R, max_pages]
  *   rope_cos/sin fp32 [>= sk_bound, head_dim] tables (cos/sin of cat(freqs, freqs), Qwen3RotaryEmbedding)
- *   out         final-RMSNorm output [R*S, D] in the stream dtype; out_add (fp32 [out_add_mod, D], stream_f32 only)
- *               is added row-wise with m % out_add_mod: h_fused = last_hidden_state + pos_embed (t2i_pipeline.py:245)
+ *   out         final-RMSNorm output [R*S, D] in the stream dtype, or fp32 when out_add is given: out_add (fp32
+ *               [out_add_mod, D]) is added row-wise with m % out_add_mod: h_fused = last_hidden_state + pos_embed
+ *               (t2i_pipeline.py:245)
  * Rounding policy: oracle/llm.py. */
 int bd_llm_forward(const bd_llm_weights_t* w, void* hidden, int stream_f32, int R, int S, int* seq_lens, int sk_bound,
                    int causal, void* kv_pool, int64_t kv_layer_stride, int64_t kv_v_offset, const int32_t* page_table,
@@ -195,6 +205,46 @@ int bd_llm_forward(const bd_llm_weights_t* w, void* hidden, int stream_f32, int 
                    int out_add_mod, int attn_splits, void* workspace, size_t workspace_bytes, int flags,
                    bd_stream_t stream);
 size_t bd_llm_workspace_bytes(const bd_llm_weights_t* w, int R, int S, int attn_splits);
+
+/* ------------------------------------------------------------------------------------------------
+ * Binary tokenizer (conv encoder / decoder) building blocks — all activations NHWC
+ * ---------------------------------------------------------------------------------------------- */
+
+/* nn.Conv2d (3x3 pad 1 stride 1|2, or 1x1) as an implicit GEMM on tcgen05 (autoencoder.py:31-38,72-77,94,105,142,170,240).
+ *   x        bf16 NHWC [B, H_out, W_out, Cin] (stride 1) or the 4-phase split [4, B, H_out, W_out, Cin] (stride 2,
+ *            bd_phase_split_nhwc); Cin % 8 == 0 (pad the 3-channel image to 8)
+ *   w_packed bf16 [Cout, k*k*Cin]: element (co, tap, ci) of weight.permute(0,2,3,1)
+ *   bias     bf16 [Cout] or NULL;  res [B,H,W,Cout] bf16/fp32 or NULL (ResBlock: x + residual, :57)
+ *   out_mode 0: NHWC [B,H,W,Cout] bf16/fp32 (out_f32) = res + bf16(acc + bias)
+ *            1: depth_to_space(2) scatter (Upsampler, :198-249): bf16 [B, 2H, 2W, Cout/4]
+ *            2: NCHW [B, Cout, H, W] (decoder conv_out -> image) */
+int bd_conv2d_nhwc(const void* x, const void* w_packed, const void* bias, const void* res, int res_f32, void* out,
+                   int out_f32, int out_mode, int B, int H_out, int W_out, int Cin, int Cout, int ksize, int stride,
+                   int flags, bd_stream_t stream);
+/* x bf16 [B, 2H, 2W, C] -> [4, B, H, W, C], phase 2a+b = x[:, 2y+a, 2x+b, :]. */
+int bd_phase_split_nhwc(const void* x, void* out, int B, int H_out, int W_out, int C, bd_stream_t stream);
+
+/* fp32 NCHW image -> bf16 NHWC with channels zero-padded to C_pad (the autocast input cast of Encoder.conv_in). */
+int bd_nchw_to_nhwc_bf16(const float* x, void* out, int B, int C, int H, int W, int C_pad, bd_stream_t stream);
+/* tokens fp32 [B, h*w, C] in patch-raster order -> bf16 NHWC [B, h, w, C]
+ * ('b (h w p1 p2) c -> b c (h p1) (w p2)', modeling/t2i_pipeline.py:280). */
+int bd_tokens_to_grid(const float* tokens, void* out, int B, int h, int w, int C, int ps, bd_stream_t stream);
+/* fp32 -> bf16 (round to nearest even): the autocast input cast of a conv / Linear fed from an fp32 tensor. */
+int bd_cast_f32_bf16(const float* x, void* out, long long n, bd_stream_t stream);
+int bd_nhwc_to_nchw(const void* x_bf16, void* out, int out_f32, int B, int C, int H, int W, bd_stream_t stream);
+
+/* nn.GroupNorm(32, C, eps) over NHWC x [B, HW, C] (bf16 or fp32), statistics in fp32 (two-stage, deterministic).
+ *   mode 0: out bf16 = swish(gn(x) * weight[c] + bias[c])   (ResBlock.forward :44-49, norm_out + swish :124-125,191-192)
+ *   mode 1: out fp32 = gn(x) * weight[b,c] + bias[b,c]       (AdaptiveGroupNorm :274-275; weight/bias from bd_adagn_params)
+ * C must be 8 * 2^k in [32, 2048]. */
+int bd_groupnorm_nhwc(const void* x, int x_f32, int B, long long HW, int C, const float* weight, const float* bias,
+                      int mode, void* out, void* workspace, size_t workspace_bytes, float eps, int flags,
+                      bd_stream_t stream);
+size_t bd_groupnorm_workspace_bytes(int B, long long HW);
+/* AdaptiveGroupNorm scale/bias (autoencoder.py:263-272): gamma = Linear(sqrt(var_unbiased(z) + 1e-6)),
+ * beta = Linear(mean(z)) over the +-1 grid z (bf16 NHWC [B, hw, Cz]); outputs fp32 [B, C] holding bf16 values. */
+int bd_adagn_params(const void* z, int B, int hw, int Cz, const void* gamma_w, const void* gamma_b, const void* beta_w,
+                    const void* beta_b, int C, float* gamma, float* beta, bd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -132,10 +132,43 @@ def sampler_schedule(num_sampling_steps: int, last_step_size: float = 0.05, time
     return ts, [dt[i] for i in range(num_sampling_steps)]
 
 
+def _cfg_combine(v, cfg, mult):
+    if mult == 2:
+        vc, vu = v.chunk(2, dim=0)
+        return vu + cfg * (vc - vu)
+    return v
+
+
+def sde_step(x, out, t, dt, cfg, mult, eps):
+    """One euler_maruyama_step (sampling_x.py:33-41) given the network output ``out`` for cat([x]*mult) at time t."""
+    comb = torch.cat([x] * mult, dim=0)
+    tb = torch.full((comb.shape[0],), float(t), dtype=torch.float32)
+    v = (out - comb) / (1 - tb.view(-1, 1, 1)).clamp_min(0.05)
+    v = _cfg_combine(v.float(), cfg, mult)
+    # get_score_from_velocity (:6-14): alpha=t, sigma=1-t, var = sigma^2 + t*sigma
+    sigma = 1 - t
+    var = sigma ** 2 - (t / 1) * (-1) * sigma
+    score = ((t / 1) * v - x) / var
+    drift = v + (1 - t) * score
+    noise_scale = (2.0 * (1.0 - t) * dt) ** 0.5
+    return x + drift * dt + noise_scale * eps.float()
+
+
+def final_step(x, out, cfg, mult, last_step_size=0.05):
+    """The deterministic last Euler step (sampling_x.py:84-95) at t = 1 - last_step_size."""
+    comb = torch.cat([x] * mult, dim=0)
+    tb = torch.full((comb.shape[0],), 1 - last_step_size, dtype=torch.float32)
+    v = (out - comb) / (1 - tb.view(-1, 1, 1)).clamp_min(0.05)
+    v = _cfg_combine(v.float(), cfg, mult)
+    return x + v * last_step_size
+
+
 def euler_maruyama(sd, c, cfg, num_sampling_steps, noise, *, rnd=ident, head_dim=128, out_sigmoid=True,
-                   last_step_size=0.05, time_shift=1.0, ch_target=None, trace=None):
+                   last_step_size=0.05, time_shift=1.0, ch_target=None, trace=None, forced_out=None):
     """sampling_x.euler_maruyama with the noise supplied: noise[0] is x0 (torch.randn at :60), noise[1+i] is the
-    randn_like of step i (:40). c: [R,pn,Dz] (cond rows first, then uncond rows when cfg > 1). Returns cat[x]*mult."""
+    randn_like of step i (:40). c: [R,pn,Dz] (cond rows first, then uncond rows when cfg > 1). Returns cat[x]*mult.
+    ``forced_out`` (list of S+1 tensors) teacher-forces the sampler with externally computed network outputs while the
+    oracle's own output for the same input is still recorded in ``trace``."""
     mult = 2 if cfg > 1.0 else 1
     x = noise[0].float().clone()
     ts, dts = sampler_schedule(num_sampling_steps, last_step_size, time_shift)
@@ -143,34 +176,15 @@ def euler_maruyama(sd, c, cfg, num_sampling_steps, noise, *, rnd=ident, head_dim
 
     def net(xx, tval):
         tb = torch.full((c.shape[0],), float(tval), dtype=torch.float32)
-        return head_forward(sd, xx, tb, c, rnd=rnd, head_dim=head_dim, out_sigmoid=out_sigmoid, c_emb=c_emb), tb
+        return head_forward(sd, xx, tb, c, rnd=rnd, head_dim=head_dim, out_sigmoid=out_sigmoid, c_emb=c_emb)
 
-    def cfg_combine(v):
-        if mult == 2:
-            vc, vu = v.chunk(2, dim=0)
-            return vu + cfg * (vc - vu)
-        return v
-
-    for i in range(num_sampling_steps):
-        t, dt = ts[i], dts[i]
-        comb = torch.cat([x] * mult, dim=0)
-        out, tb = net(comb, t)
-        v = (out - comb) / (1 - tb.view(-1, 1, 1)).clamp_min(0.05)
-        v = cfg_combine(v.float())
-        # get_score_from_velocity (:6-14): alpha=t, sigma=1-t, var = sigma^2 + t*sigma
-        sigma = 1 - t
-        var = sigma ** 2 - (t / 1) * (-1) * sigma
-        score = ((t / 1) * v - x) / var
-        drift = v + (1 - t) * score
-        noise_scale = (2.0 * (1.0 - t) * dt) ** 0.5
-        x = x + drift * dt + noise_scale * noise[1 + i].float()
+    for i in range(num_sampling_steps + 1):
+        last = i == num_sampling_steps
+        out = net(torch.cat([x] * mult, dim=0), (1 - last_step_size) if last else ts[i])
         if trace is not None:
-            trace.append(dict(out=out.clone(), x=x.clone()))
-    comb = torch.cat([x] * mult, dim=0)
-    out, tb = net(comb, 1 - last_step_size)
-    v = (out - comb) / (1 - tb.view(-1, 1, 1)).clamp_min(0.05)
-    v = cfg_combine(v.float())
-    x = x + v * last_step_size
-    if trace is not None:
-        trace.append(dict(out=out.clone(), x=x.clone()))
+            trace.append(dict(out=out.clone(), x_in=x.clone()))
+        if forced_out is not None:
+            out = forced_out[i].float()
+        x = final_step(x, out, cfg, mult, last_step_size) if last else sde_step(x, out, ts[i], dts[i], cfg, mult,
+                                                                                 noise[1 + i])
     return torch.cat([x] * mult, dim=0)

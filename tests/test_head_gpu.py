@@ -34,24 +34,27 @@ def test_head_sample_vs_oracle(cfg, B, pn, guidance, S):
     noise = torch.randn(S + 1, B, pn, cfg["ch_target"])
     x, trace = runner.sample(z.cuda(), guidance, S, noise=noise.cuda(), trace=True)
     torch.cuda.synchronize()
+    hd, osig = cfg.get("head_dim", 128), cfg.get("out_sigmoid", True)
+    # (1) teacher-forced parity: drive the oracle sampler with the GPU's own network outputs. Then
+    #   * at every evaluation the oracle network sees exactly the state the GPU saw: outputs must agree to a few
+    #     bf16 ulps (accumulation order, fast exp);
+    #   * the fp32 sampler arithmetic itself must reproduce the GPU state essentially exactly.
     tr = []
-    ref = oh.euler_maruyama(sd, z, guidance, S, list(noise), rnd=oh.bf16, head_dim=cfg.get("head_dim", 128),
-                            out_sigmoid=cfg.get("out_sigmoid", True), trace=tr)
-    ref = ref[:B]
-    # first network evaluation: same inputs on both sides -> only accumulation-order / exp differences
-    out0 = trace[0].cpu().view(B * mult, pn, -1)
-    e0 = (out0 - tr[0]["out"]).abs().max().item()
-    assert e0 < 3e-2, f"first eval err {e0}"
-    # whole sampler. The last Euler step gives x_final = out_u + cfg*(out_c - out_u) (+ the carried state), so one
-    # bf16 ulp (2^-8 near |out| ~ 1) of disagreement in a network output moves x_final by up to (1 + 2 cfg) ulps;
-    # the max over pn*C elements is therefore bounded by a few such flips, while the MEAN error stays at rounding level.
+    forced = [trace[i].cpu().view(B * mult, pn, -1) for i in range(S + 1)]
+    x_tf = oh.euler_maruyama(sd, z, guidance, S, list(noise), rnd=oh.bf16, head_dim=hd, out_sigmoid=osig, trace=tr,
+                             forced_out=forced)[:B]
+    scale = max(1.0, max(t["out"].abs().max().item() for t in tr))
+    e_net = max((forced[i] - tr[i]["out"]).abs().max().item() for i in range(S + 1))
+    e_sde = (x.cpu() - x_tf).abs().max().item()
+    # (2) free-running: chaotic amplification of those ulps through the SDE (reported, loosely bounded)
+    ref = oh.euler_maruyama(sd, z, guidance, S, list(noise), rnd=oh.bf16, head_dim=hd, out_sigmoid=osig)[:B]
     d = (x.cpu() - ref).abs()
     agree = (torch.sign(x.cpu()) == torch.sign(ref)).float().mean().item()
-    print(f"head parity: first-eval max {e0:.4f}  final max {d.max().item():.4f} mean {d.mean().item():.5f} "
-          f"sign agreement {agree:.4f}")
-    assert d.mean().item() < 0.02, f"final x mean err {d.mean().item()}"
-    assert d.max().item() < 0.06 * (1 + 2 * guidance), f"final x max err {d.max().item()}"
-    assert agree > 0.97, f"sign agreement {agree}"
+    print(f"head parity: teacher-forced net max err {e_net:.4f} (scale {scale:.2f}), sampler err {e_sde:.2e}; "
+          f"free-running max {d.max().item():.4f} mean {d.mean().item():.5f} sign agreement {agree:.4f}")
+    assert e_net < 4.7e-2 * scale, f"network output err {e_net}"   # 6 bf16 ulps at |out| ~ 1 (2^-8 spacing)
+    assert e_sde < 1e-4 * max(1.0, x_tf.abs().max().item()), f"sampler arithmetic err {e_sde}"
+    assert agree > 0.95, f"free-running sign agreement {agree}"
 
 
 def test_head_sampler_deterministic_and_seeded_noise():

@@ -1,0 +1,192 @@
+"""Pin the CPU oracle (oracle/*.py) against the UNMODIFIED reference imported from /root/reference.
+
+The reference ships no tests or golden vectors, so its own code run on CPU in fp32 is the pin. These
+tests run in the dev container only (marker ``reference``); on the GPU box the oracle is used as pinned here."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_harness as rh
+    return rh.import_reference()
+
+
+def _capture_noise(fn):
+    """Run fn() while recording every torch.randn / randn_like result, in call order."""
+    rec = []
+    o1, o2 = torch.randn, torch.randn_like
+
+    def r1(*a, **k):
+        t = o1(*a, **k)
+        rec.append(t.clone())
+        return t
+
+    def r2(a, **k):
+        t = o2(a, **k)
+        rec.append(t.clone())
+        return t
+
+    torch.randn, torch.randn_like = r1, r2
+    try:
+        out = fn()
+    finally:
+        torch.randn, torch.randn_like = o1, o2
+    return out, rec
+
+
+def test_quantiser_and_gfq_vs_reference(ref):
+    import sys
+    sys.path.insert(0, "/root/reference/imagenet_gen")
+    from src.gfq import GFQ
+    from oracle import quant as oq
+    torch.manual_seed(0)
+    h = torch.randn(2, 32, 5, 7)
+    h[0, 0, 0, 0] = 0.0
+    gfq = GFQ(dim=32, num_codebooks=4).eval()
+    with torch.no_grad():
+        quant, _, idx_list = gfq(h)
+    assert np.array_equal(quant.numpy(), oq.sign_quantize(h.numpy()))
+    mine = oq.gfq_indices(h.numpy(), 4)
+    for g in range(4):
+        assert np.array_equal(idx_list[g].numpy().astype(np.int32), mine[g])
+    # VQModel.encode's rule and torch.sign
+    cb = torch.tensor([1.0])
+    assert np.array_equal(torch.where(h > 0, cb, -cb).numpy(), oq.sign_quantize(h.numpy()))
+    x = torch.tensor([0.0, -0.0, float("nan"), 2.0, -3.0])
+    assert np.array_equal(torch.sign(x).numpy(), oq.sign_lfq(x.numpy()))
+
+
+@pytest.mark.parametrize("swiglu,pn", [(True, 16), (True, 64), (False, 4)])
+def test_head_and_sampler_vs_reference(ref, swiglu, pn):
+    from bitdance_b200.head import head_spec
+    from bitdance_b200.synth import synth_state_dict
+    from oracle import head as oh
+    cfg = dict(ch_target=32, ch_cond=96, ch_latent=128, depth_latent=4, depth_adanln=2, parallel_num=pn, use_swiglu=swiglu)
+    m = ref.fh.DiffHead(**cfg).eval()
+    spec = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert spec == head_spec(32, 96, 128, 4, 2, swiglu)
+    sd = synth_state_dict(spec, seed=1, std=0.05)
+    m.load_state_dict(sd)
+    torch.manual_seed(0)
+    R = 4
+    x, t, c = torch.randn(R, pn, 32), torch.rand(R), torch.randn(R, pn, 96)
+    with torch.no_grad():
+        assert (m.net(x, t, c) - oh.head_forward(sd, x, t, c)).abs().max().item() < 2e-5
+        for cfg_scale in (1.0, 3.0):
+            out, noise = _capture_noise(lambda: m.sample(c, cfg=cfg_scale, num_sampling_steps=6))
+            mine = oh.euler_maruyama(sd, c, cfg_scale, 6, noise)
+            assert (out - mine).abs().max().item() < 2e-4
+
+
+def test_llm_vs_transformers(ref):
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    from bitdance_b200.llm import llm_spec
+    from bitdance_b200.synth import synth_state_dict
+    from oracle import llm as ol
+    c = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+             head_dim=64, rms_norm_eps=1e-6, rope_theta=1e6)
+    hf = Qwen3ForCausalLM(Qwen3Config(vocab_size=64, max_position_embeddings=512, tie_word_embeddings=False, **c)).eval()
+    spec = {k: tuple(v.shape) for k, v in hf.state_dict().items()}
+    assert all(spec[k] == v for k, v in llm_spec(c).items())
+    sd = synth_state_dict(spec, seed=3, std=0.05)
+    hf.load_state_dict(sd)
+    torch.manual_seed(0)
+    B, pn = 2, 16
+    xs = [torch.randn(B, 9, 128), torch.randn(B, pn, 128), torch.randn(B, pn, 128)]
+    cache = [None] * 2
+    with torch.no_grad():
+        o = hf.model(inputs_embeds=xs[0], use_cache=True)
+        pkv = o.past_key_values
+        assert (o.last_hidden_state - ol.decoder_forward(sd, c, xs[0], cache, causal=True)).abs().max() < 2e-5
+        for x in xs[1:]:
+            mask = torch.ones(B, 1, pn, pn + pkv[0][0].shape[2], dtype=torch.bool)
+            o = hf.model(inputs_embeds=x, past_key_values=pkv, use_cache=True, attention_mask=mask)
+            pkv = o.past_key_values
+            assert (o.last_hidden_state - ol.decoder_forward(sd, c, x, cache, causal=False)).abs().max() < 2e-5
+
+
+def test_autoencoder_vs_reference(ref):
+    from bitdance_b200.ae import ae_spec
+    from bitdance_b200.synth import synth_state_dict
+    from oracle import ae as oa
+    dd = dict(double_z=False, z_channels=32, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2], num_res_blocks=2)
+    m = ref.ae.VQModel(dd).eval()
+    spec = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert spec == ae_spec(dd)
+    sd = synth_state_dict(spec, seed=2, std=0.05)
+    m.load_state_dict(sd)
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 32, 48) * 2 - 1
+    with torch.no_grad():
+        q_ref = m.encode(x)
+        d_ref = m.decode(q_ref)
+        q, _ = oa.encode(sd, x)
+        assert torch.equal(q, q_ref)                       # token grid: bit-exact
+        assert (oa.decoder_forward(sd, q) - d_ref).abs().max().item() < 1e-4
+
+
+def test_pipeline_vs_reference(ref):
+    """Whole gen_image: tiny Qwen3 + head + projector + tokenizer, stub tokenizer, CFG on, 2 images."""
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    from bitdance_b200.synth import synth_state_dict
+    from oracle import pipeline as op
+    pn, S, B, guidance = 16, 4, 2, 3.0
+    c = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+             head_dim=64, rms_norm_eps=1e-6, rope_theta=1e6)
+    hf = Qwen3ForCausalLM(Qwen3Config(vocab_size=200, max_position_embeddings=2048, tie_word_embeddings=False, **c)).eval()
+    sd_llm = synth_state_dict({k: tuple(v.shape) for k, v in hf.state_dict().items()}, seed=3, std=0.05)
+    hf.load_state_dict(sd_llm)
+    head = ref.fh.DiffHead(ch_target=32, ch_cond=128, ch_latent=128, depth_latent=2, depth_adanln=2, parallel_num=pn,
+                           use_swiglu=True).eval()
+    sd_head = synth_state_dict({k: tuple(v.shape) for k, v in head.state_dict().items()}, seed=1, std=0.05)
+    head.load_state_dict(sd_head)
+    dd = dict(double_z=False, z_channels=32, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2], num_res_blocks=1)
+    ae = ref.ae.VQModel(dd).eval()
+    sd_ae = synth_state_dict({k: tuple(v.shape) for k, v in ae.state_dict().items()}, seed=2, std=0.05)
+    ae.load_state_dict(sd_ae)
+    proj = ref.mu.MLPconnector(32, 128, "gelu_pytorch_tanh").eval()
+    sd_proj = synth_state_dict({k: tuple(v.shape) for k, v in proj.state_dict().items()}, seed=4, std=0.05)
+    proj.load_state_dict(sd_proj)
+
+    class Tok:
+        special = {"<|vision_start|>": 150}
+
+        def encode(self, s):
+            return [ord(ch) % 100 for ch in s][:12] if s == "cond" else [7, 8, 9]
+
+        def convert_tokens_to_ids(self, t):
+            if t in self.special:
+                return self.special[t]
+            if t.startswith("<|res_"):
+                return 151 + int(t[6:-2]) % 20
+            return 172 + int(t[8:-2])  # <|query_i|>
+
+    P = ref.t2i.BitDanceT2IPipeline
+    pipe = object.__new__(P)
+    pipe.device, pipe.tokenizer, pipe.llm_model = "cpu", Tok(), hf
+    pipe.hidden_size, pipe.ae, pipe.vision_head, pipe.embed_vision_mlp = 128, ae, head, proj
+    pipe.vae_patch_size, pipe.parallel_num, pipe.ps = 4, pn, 4
+    pipe.build_pos_embed(max_len=1024)
+    Himg = Wimg = 32  # 8 x 8 latent = 64 tokens = 4 AR steps
+    torch.manual_seed(11)
+    with torch.no_grad():
+        img_ref, noise = _capture_noise(lambda: pipe.gen_image("cond", "uncond", guidance_scale=guidance,
+                                                               num_sampling_steps=S, max_length=64, num_images=B,
+                                                               image_size=[Himg, Wimg]))
+    steps = 64 // pn
+    assert len(noise) == steps * (S + 1)
+    per_step = [noise[i * (S + 1):(i + 1) * (S + 1)] for i in range(steps)]
+    tok = Tok()
+    start = [tok.convert_tokens_to_ids("<|vision_start|>"), tok.convert_tokens_to_ids("<|res_8|>"),
+             tok.convert_tokens_to_ids("<|res_8|>")] + [tok.convert_tokens_to_ids(f"<|query_{i}|>") for i in range(1, pn)]
+    with torch.no_grad():
+        tokens, img = op.gen_image(sd_llm=sd_llm, cfg_llm=c, embed=sd_llm["model.embed_tokens.weight"], sd_head=sd_head,
+                                   sd_proj=sd_proj, sd_ae=sd_ae, cond_ids=tok.encode("cond"), uncond_ids=tok.encode("u"),
+                                   start_ids=start, h=8, w=8, pn=pn, num_images=B, guidance=guidance, S=S,
+                                   noise=per_step, head_dim=128)
+    assert img.shape == img_ref.shape == (B, 3, Himg, Wimg)
+    assert (img - img_ref).abs().max().item() < 1e-3 * max(1.0, img_ref.abs().max().item())
