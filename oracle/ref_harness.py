@@ -29,47 +29,67 @@ def _eager_flash(q, k, v, causal=False):
 
 
 _done = False
+_ns = None
 
 
 def import_reference():
-    """Returns a namespace with the reference modules; applies the shims once."""
-    global _done
+    """Returns a namespace with the reference modules; applies the shims once. The reference's top-level package is
+    called ``modeling`` — the same name as this repo's drop-in package — so it is imported with /root/reference first
+    on sys.path and then moved out of ``sys.modules`` (the namespace keeps the module objects alive)."""
+    global _done, _ns
     if not available():
         raise RuntimeError("/root/reference not present")
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    if _ns is not None:
+        return _ns
     import types
 
-    if not _done:
-        # shim A must be in place before flow_head_parallel_x is imported on a box without flash_attn CPU kernels
-        try:
-            import flash_attn  # noqa: F401
-        except Exception:
-            m = types.ModuleType("flash_attn")
-            m.flash_attn_func = _eager_flash
-            sys.modules["flash_attn"] = m
-    import modeling.vision_head.flow_head_parallel_x as fh
-    import modeling.vision_head.sampling_x as sx
-    import modeling.vision_encoder.autoencoder as ae
-    import modeling.utils as mu
-    import modeling.t2i_pipeline as t2i
+    try:
+        import flash_attn  # noqa: F401
+    except Exception:
+        m = types.ModuleType("flash_attn")
+        m.flash_attn_func = _eager_flash
+        sys.modules["flash_attn"] = m
+    mine = {k: v for k, v in sys.modules.items() if k == "modeling" or k.startswith("modeling.")}
+    for k in mine:
+        del sys.modules[k]
+    # this repo's ``modeling`` is a regular package and would win over the reference's namespace package no matter
+    # the sys.path order: hide the repo root (and cwd) while importing the reference
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hidden = [(i, p) for i, p in enumerate(sys.path) if os.path.abspath(p or os.getcwd()) == repo_root]
+    for _, p in hidden:
+        sys.path.remove(p)
+    sys.path.insert(0, REF)
+    try:
+        import modeling.vision_head.flow_head_parallel_x as fh
+        import modeling.vision_head.sampling_x as sx
+        import modeling.vision_encoder.autoencoder as ae
+        import modeling.utils as mu
+        import modeling.t2i_pipeline as t2i
+    finally:
+        sys.path.remove(REF)
+        for i, p in hidden:
+            sys.path.insert(min(i, len(sys.path)), p)
+        for k in [k for k in sys.modules if k == "modeling" or k.startswith("modeling.")]:
+            del sys.modules[k]
+        sys.modules.update(mine)
+    if REF not in sys.path:
+        sys.path.append(REF)  # the reference's own `utils.fs` etc. stay importable, behind this repo's packages
 
-    if not _done:
-        fh.flash_attn_func = _eager_flash
-        from transformers import DynamicCache
-        from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+    fh.flash_attn_func = _eager_flash
+    from transformers import DynamicCache
+    from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
 
-        if not hasattr(DynamicCache, "_bd_shim"):
-            DynamicCache.__getitem__ = lambda s, i: (s.layers[i].keys, s.layers[i].values)
-            DynamicCache._bd_shim = True
-            _orig = ALL_ATTENTION_FUNCTIONS["sdpa"]
+    if not hasattr(DynamicCache, "_bd_shim"):
+        DynamicCache.__getitem__ = lambda s, i: (s.layers[i].keys, s.layers[i].values)
+        DynamicCache._bd_shim = True
+        _orig = ALL_ATTENTION_FUNCTIONS["sdpa"]
 
-            def _sdpa(module, q, k, v, attention_mask=None, **kw):
-                if attention_mask is not None and attention_mask.dim() == 4:
-                    attention_mask = attention_mask[..., : k.shape[-2]]
-                return _orig(module, q, k, v, attention_mask=attention_mask, **kw)
+        def _sdpa(module, q, k, v, attention_mask=None, **kw):
+            if attention_mask is not None and attention_mask.dim() == 4:
+                attention_mask = attention_mask[..., : k.shape[-2]]
+            return _orig(module, q, k, v, attention_mask=attention_mask, **kw)
 
-            ALL_ATTENTION_FUNCTIONS["sdpa"] = _sdpa
-        _done = True
-    ns = types.SimpleNamespace(fh=fh, sx=sx, ae=ae, mu=mu, t2i=t2i)
-    return ns
+        ALL_ATTENTION_FUNCTIONS["sdpa"] = _sdpa
+    _done = True
+    _ns = types.SimpleNamespace(fh=fh, sx=sx, ae=ae, mu=mu, t2i=t2i)
+    return _ns
