@@ -32,7 +32,7 @@ static GemmPlan plan_gemm(int M, int N, int K, int bn, int splits) {
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, int splits, float* partial,
-                       const GemmEpi& epi, bool pdl, cudaStream_t stream) {
+                       const GemmEpi& epi, bool pdl, cudaStream_t stream, int w_tiled) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -43,7 +43,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, int M, int 
   LaunchCfg lc(grid, dim3(kGemmThreads), Cfg::kSmemBytes, stream, pdl);
   // Re-reading A across N tiles should hit L2: ask TMA to keep it when it is small next to W.
   const int a_hint_last = (static_cast<long long>(M) * K * 2 <= (32ll << 20)) ? 1 : 0;
-  BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, bd_gemm_kernel<BN>, ta, tw, M, N, K, splits, partial, epi, a_hint_last));
+  BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, bd_gemm_kernel<BN>, ta, tw, M, N, K, splits, partial, epi, a_hint_last, w_tiled));
   return BD_OK;
 }
 
@@ -60,6 +60,29 @@ __global__ void bd_interleave16_kernel(const __nv_bfloat16* __restrict__ gate, c
   if (threadIdx.x == 0 && bo) bo[r] = (w < 16 ? bg : bu)[src];
 }
 
+// W [N, K] row-major (ld) -> tile-major [ceil(N/128)][ceil(K/64)][128][64], zero padded. One CTA per tile row.
+__global__ void __launch_bounds__(256) pack_weight_tiles_kernel(const __nv_bfloat16* __restrict__ w, long long ldw, int N,
+                                                                int K, __nv_bfloat16* __restrict__ out) {
+  const int KB = (K + 63) / 64;
+  const long long tile = blockIdx.x;           // nt * KB + kb
+  const int nt = static_cast<int>(tile / KB), kb = static_cast<int>(tile % KB);
+  for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {  // 16-byte chunks of the tile
+    const int r = i >> 3, c8 = (i & 7) * 8;
+    const int n = nt * 128 + r, k = kb * 64 + c8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < N) {
+      if (k + 8 <= K && ((ldw & 7) == 0)) {
+        v = *reinterpret_cast<const uint4*>(w + n * ldw + k);
+      } else {
+        __nv_bfloat16 t[8];
+        for (int j = 0; j < 8; ++j) t[j] = (k + j < K) ? w[n * ldw + k + j] : __float2bfloat16_rn(0.f);
+        v = *reinterpret_cast<uint4*>(t);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (tile * 128 + r) * 64 + c8) = v;
+  }
+}
+
 size_t gemm_workspace_bytes(int M, int N, int K, int bn, int splits) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   GemmPlan p = plan_gemm(M, N, K, bn, splits);
@@ -67,8 +90,10 @@ size_t gemm_workspace_bytes(int M, int N, int K, int bn, int splits) {
 }
 
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const GemmEpi& epi,
-              void* workspace, size_t workspace_bytes, int bn, int splits, bool pdl, cudaStream_t stream) {
+              void* workspace, size_t workspace_bytes, int bn, int splits, bool pdl, cudaStream_t stream,
+              bool w_tiled) {
   BD_REQUIRE(A && W && epi.out);
+  if (w_tiled) ldw = ((K + 63) / 64) * 64;
   BD_REQUIRE(M > 0 && N > 0 && K > 0);
   BD_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 256);
   BD_REQUIRE(splits >= 0);
@@ -86,13 +111,19 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   int rc = make_tmap_2d_bf16(&ta, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda),
                              kGemmBK, kGemmBM);
   if (rc != BD_OK) return rc;
-  rc = make_tmap_2d_bf16(&tw, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw),
-                         kGemmBK, static_cast<uint32_t>(p.bn));
+  if (w_tiled) {
+    const uint64_t rows = static_cast<uint64_t>((N + 127) / 128) * ((K + 63) / 64) * 128;
+    rc = make_tmap_2d_bf16(&tw, W, 64, rows, 64, kGemmBK, static_cast<uint32_t>(p.bn < 128 ? p.bn : 128));
+  } else {
+    rc = make_tmap_2d_bf16(&tw, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw),
+                           kGemmBK, static_cast<uint32_t>(p.bn));
+  }
   if (rc != BD_OK) return rc;
+  const int wt = w_tiled ? 1 : 0;
   switch (p.bn) {
-    case 64: rc = launch_gemm<64>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream); break;
-    case 128: rc = launch_gemm<128>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream); break;
-    default: rc = launch_gemm<256>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream); break;
+    case 64: rc = launch_gemm<64>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream, wt); break;
+    case 128: rc = launch_gemm<128>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream, wt); break;
+    default: rc = launch_gemm<256>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream, wt); break;
   }
   if (rc != BD_OK) return rc;
   if (p.splits > 1) {
@@ -133,7 +164,22 @@ int bd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, 
   epi.out_f32 = e->out_f32;
   epi.res_mod = e->res_row_mod;
   return gemm_bf16(A, lda, W, ldw, M, N, K, epi, workspace, workspace_bytes, bn, splits, (flags & 1) != 0,
-                   static_cast<cudaStream_t>(stream_));
+                   static_cast<cudaStream_t>(stream_), (flags & 2) != 0);
+}
+
+size_t bd_packed_weight_elems(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  return static_cast<size_t>((N + 127) / 128) * ((K + 63) / 64) * 128 * 64;
+}
+
+int bd_pack_weight_tiles(const void* W, int64_t ldw, int N, int K, void* out, bd_stream_t stream) {
+  BD_REQUIRE(W && out && N > 0 && K > 0 && ldw >= K);
+  BD_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long tiles = static_cast<long long>((N + 127) / 128) * ((K + 63) / 64);
+  pack_weight_tiles_kernel<<<static_cast<unsigned>(tiles), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(W), ldw, N, K, static_cast<__nv_bfloat16*>(out));
+  BD_LAUNCH_CHECK();
+  return BD_OK;
 }
 
 int bd_interleave16(const void* gate, const void* up, void* out, int F, int K, const void* bias_gate,

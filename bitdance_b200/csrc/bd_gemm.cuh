@@ -110,7 +110,7 @@ struct GemmCfg {
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M, int N,
-               int K, int splits, float* __restrict__ partial, GemmEpi epi, int a_hint_last) {
+               int K, int splits, float* __restrict__ partial, GemmEpi epi, int a_hint_last, int w_tiled) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -146,6 +146,21 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // Let the next kernel in the stream begin its own prologue / weight prefetch as SMs free up.
   grid_dep_launch();
 
+  // W tile of k-block kb into stage memory. Row-major W: one strided box (BN rows x 128 B, rows K*2 bytes apart).
+  // Tile-major W (bd_pack_weight_tiles: [n_tile][k_block][128][64], every 128x64 tile = 16 KB CONTIGUOUS in HBM, the
+  // k-blocks of one n_tile adjacent): each CTA streams one contiguous region — DRAM-page friendly.
+  auto load_w = [&](uint8_t* dst, uint64_t* bar, int kb) {
+    if (!w_tiled) {
+      tma_load_2d(dst, &tmap_w, bar, kb * kGemmBK, n0, kEvictFirst);
+    } else if (BN >= 128) {
+#pragma unroll
+      for (int hh = 0; hh < BN / 128; ++hh)
+        tma_load_2d(dst + hh * (128 * kGemmBK * 2), &tmap_w, bar, 0, ((n0 / 128 + hh) * num_kb + kb) * 128, kEvictFirst);
+    } else {
+      tma_load_2d(dst, &tmap_w, bar, 0, ((n0 / 128) * num_kb + kb) * 128 + (n0 % 128), kEvictFirst);
+    }
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -154,8 +169,7 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int pre = nkb < Cfg::kStages ? nkb : Cfg::kStages;
       for (int i = 0; i < pre; ++i) {
         mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
-        tma_load_2d(smem + i * Cfg::kStageBytes + Cfg::kABytes, &tmap_w, &full_bar[i], (kb_begin + i) * kGemmBK, n0,
-                    kEvictFirst);
+        load_w(smem + i * Cfg::kStageBytes + Cfg::kABytes, &full_bar[i], kb_begin + i);
       }
       grid_dep_wait();  // activations are produced by the upstream kernel
       for (int i = 0; i < pre; ++i)
@@ -166,8 +180,7 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t ph = static_cast<uint32_t>(i / Cfg::kStages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        tma_load_2d(smem + s * Cfg::kStageBytes + Cfg::kABytes, &tmap_w, &full_bar[s], (kb_begin + i) * kGemmBK, n0,
-                    kEvictFirst);
+        load_w(smem + s * Cfg::kStageBytes + Cfg::kABytes, &full_bar[s], kb_begin + i);
         tma_load_2d(smem + s * Cfg::kStageBytes, &tmap_a, &full_bar[s], (kb_begin + i) * kGemmBK, m0, a_hint);
       }
     }

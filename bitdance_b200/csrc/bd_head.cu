@@ -376,7 +376,7 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
   const int switch_freq = w.n_blocks / w.n_ada;
 
   auto gemm = [&](const void* A, long long lda, const void* W, int m, int n, int k, GemmEpi e) {
-    return gemm_bf16(A, lda, W, k, m, n, k, e, gws, gws_bytes, 0, 0, pdl, st);
+    return gemm_bf16(A, lda, W, k, m, n, k, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0);
   };
   auto bf = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
 

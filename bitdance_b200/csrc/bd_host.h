@@ -61,8 +61,10 @@ struct GemmEpi {
 
 // Internal C++ entry points shared by the composite ops (bd_head.cu, bd_llm.cu, ...).
 size_t gemm_workspace_bytes(int M, int N, int K, int bn, int splits);
+// w_tiled: W is in the tile-major layout of bd_pack_weight_tiles (ldw ignored).
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const GemmEpi& epi,
-              void* workspace, size_t workspace_bytes, int bn, int splits, bool pdl, cudaStream_t stream);
+              void* workspace, size_t workspace_bytes, int bn, int splits, bool pdl, cudaStream_t stream,
+              bool w_tiled = false);
 
 int num_sms();
 

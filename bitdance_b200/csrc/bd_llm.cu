@@ -272,7 +272,7 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
       GemmEpi e;
       e.out = qkv;
       e.ld_out = qkv_n;
-      BD_TRY(gemm_bf16(a, D, lw.wqkv, D, M, qkv_n, D, e, gws, gws_bytes, 0, 0, pdl, st));
+      BD_TRY(gemm_bf16(a, D, lw.wqkv, D, M, qkv_n, D, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0));
     }
     {
       const long long warps = static_cast<long long>(M) * (w.Hq + 2 * w.Hkv);
@@ -310,7 +310,7 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
       e.out = hidden;
       e.ld_out = D;
       e.out_f32 = stream_f32;
-      BD_TRY(gemm_bf16(o, w.Hq * hd, lw.wo, w.Hq * hd, M, D, w.Hq * hd, e, gws, gws_bytes, 0, 0, pdl, st));
+      BD_TRY(gemm_bf16(o, w.Hq * hd, lw.wo, w.Hq * hd, M, D, w.Hq * hd, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0));
     }
     BD_TRY(norm_to_bf16(lw.ln2_w));
     {
@@ -318,7 +318,7 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
       e.swiglu = 1;
       e.out = g;
       e.ld_out = w.I;
-      BD_TRY(gemm_bf16(a, D, lw.w_gate_up, D, M, 2 * w.I, D, e, gws, gws_bytes, 0, 0, pdl, st));
+      BD_TRY(gemm_bf16(a, D, lw.w_gate_up, D, M, 2 * w.I, D, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0));
     }
     {
       GemmEpi e;
@@ -328,7 +328,7 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
       e.out = hidden;
       e.ld_out = D;
       e.out_f32 = stream_f32;
-      BD_TRY(gemm_bf16(g, w.I, lw.w_down, w.I, M, D, w.I, e, gws, gws_bytes, 0, 0, pdl, st));
+      BD_TRY(gemm_bf16(g, w.I, lw.w_down, w.I, M, D, w.I, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0));
     }
   }
   if (stream_f32)

@@ -24,7 +24,8 @@ class HeadBlock(C.Structure):
 
 class HeadWeights(C.Structure):
     _fields_ = (
-        [(n, C.c_int) for n in ("D", "Dz", "C", "hidden", "n_blocks", "n_ada", "head_dim", "use_swiglu", "out_sigmoid")]
+        [(n, C.c_int) for n in ("D", "Dz", "C", "hidden", "n_blocks", "n_ada", "head_dim", "use_swiglu", "w_tiled",
+                                "out_sigmoid")]
         + [(n, C.c_void_p) for n in ("input_proj_w", "input_proj_b", "time0_w", "time0_b", "time2_w", "time2_b",
                                      "cond_w", "cond_b", "ada_w", "ada_b", "final_w", "final_b")]
         + [("blocks", HeadBlock * MAX_BLOCKS)]
@@ -117,36 +118,46 @@ class HeadRunner:
             self._keep.append(t)
             return t
 
+        def pk(t):
+            """tile-major prepack; the row-major copy is dropped"""
+            p = ops.pack_weight(t)
+            self._keep = [k for k in self._keep if k is not t]
+            self._keep.append(p.data)
+            return p.data_ptr()
+
         w = HeadWeights()
+        w.w_tiled = 1
         w.D, w.Dz, w.C, w.hidden = ch_latent, ch_cond, ch_target, self.hidden
         w.n_blocks, w.n_ada, w.head_dim = depth_latent, depth_adanln, head_dim
         w.use_swiglu, w.out_sigmoid = int(use_swiglu), int(out_sigmoid)
         for field, name in (("input_proj", "input_proj"), ("time0", "time_embed.mlp.0"), ("time2", "time_embed.mlp.2"),
                             ("cond", "cond_embed"), ("final", "final_layer.linear")):
-            setattr(w, field + "_w", bf(name + ".weight").data_ptr())
+            wt = bf(name + ".weight")
+            setattr(w, field + "_w", wt.data_ptr() if field == "final" else pk(wt))
             setattr(w, field + "_b", bf(name + ".bias").data_ptr())
         ada_names = [f"ada_ln_blocks.{i}" for i in range(depth_adanln)] + ["final_layer.ada_ln_modulation"]
-        ada_w = torch.cat([bf(n + ".weight") for n in ada_names], dim=0).contiguous()
-        ada_b = torch.cat([bf(n + ".bias") for n in ada_names], dim=0).contiguous()
-        self._keep += [ada_w, ada_b]
-        w.ada_w, w.ada_b = ada_w.data_ptr(), ada_b.data_ptr()
+        tmp = lambda name: state_dict[prefix + name].detach().to(device=dev, dtype=torch.bfloat16)
+        ada_w = torch.cat([tmp(n + ".weight") for n in ada_names], dim=0).contiguous()
+        ada_b = torch.cat([tmp(n + ".bias") for n in ada_names], dim=0).contiguous()
+        self._keep.append(ada_b)
+        w.ada_w, w.ada_b = pk(ada_w), ada_b.data_ptr()
         for i in range(depth_latent):
             b = f"res_blocks.{i}."
             blk = w.blocks[i]
             blk.norm1_w, blk.norm1_b = f32(b + "norm1.weight").data_ptr(), f32(b + "norm1.bias").data_ptr()
             blk.norm2_w, blk.norm2_b = f32(b + "norm2.weight").data_ptr(), f32(b + "norm2.bias").data_ptr()
-            blk.wqkv_w, blk.wqkv_b = bf(b + "attn.wqkv.weight").data_ptr(), bf(b + "attn.wqkv.bias").data_ptr()
-            blk.wo_w, blk.wo_b = bf(b + "attn.wo.weight").data_ptr(), bf(b + "attn.wo.bias").data_ptr()
+            blk.wqkv_w, blk.wqkv_b = pk(bf(b + "attn.wqkv.weight")), bf(b + "attn.wqkv.bias").data_ptr()
+            blk.wo_w, blk.wo_b = pk(bf(b + "attn.wo.weight")), bf(b + "attn.wo.bias").data_ptr()
             if use_swiglu:
                 w1, b1 = bf(b + "w1.weight"), bf(b + "w1.bias")
                 wi, bi = ops.interleave16(w1[: self.hidden], w1[self.hidden:], b1[: self.hidden], b1[self.hidden:])
-                self._keep += [wi, bi]
+                self._keep.append(bi)
                 self._keep = [t for t in self._keep if t is not w1]  # un-interleaved copy not needed
-                blk.w1_w, blk.w1_b = wi.data_ptr(), bi.data_ptr()
-                blk.w2_w, blk.w2_b = bf(b + "w2.weight").data_ptr(), bf(b + "w2.bias").data_ptr()
+                blk.w1_w, blk.w1_b = pk(wi), bi.data_ptr()
+                blk.w2_w, blk.w2_b = pk(bf(b + "w2.weight")), bf(b + "w2.bias").data_ptr()
             else:
-                blk.w1_w, blk.w1_b = bf(b + "mlp.0.weight").data_ptr(), bf(b + "mlp.0.bias").data_ptr()
-                blk.w2_w, blk.w2_b = bf(b + "mlp.2.weight").data_ptr(), bf(b + "mlp.2.bias").data_ptr()
+                blk.w1_w, blk.w1_b = pk(bf(b + "mlp.0.weight")), bf(b + "mlp.0.bias").data_ptr()
+                blk.w2_w, blk.w2_b = pk(bf(b + "mlp.2.weight")), bf(b + "mlp.2.bias").data_ptr()
         torch.cuda.synchronize(dev)
         self.w = w
         self._ws = None

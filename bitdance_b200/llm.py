@@ -22,7 +22,7 @@ class LlmLayer(C.Structure):
 
 class LlmWeights(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("D", "I", "n_layers", "Hq", "Hkv", "head_dim")] + [
-        ("eps", C.c_float), ("final_norm_w", C.c_void_p), ("layers", C.POINTER(LlmLayer))]
+        ("eps", C.c_float), ("w_tiled", C.c_int), ("final_norm_w", C.c_void_p), ("layers", C.POINTER(LlmLayer))]
 
 
 def llm_config_dict(cfg) -> dict:
@@ -110,6 +110,7 @@ class LlmRunner:
             wo = get(p + "self_attn.o_proj.weight", (D, Hq * hd))
             wgu, _ = ops.interleave16(get(p + "mlp.gate_proj.weight", (I, D)), get(p + "mlp.up_proj.weight", (I, D)))
             wd = get(p + "mlp.down_proj.weight", (D, I))
+            wqkv, wo, wgu, wd = (ops.pack_weight(t).data for t in (wqkv, wo, wgu, wd))  # tile-major for HBM streaming
             keep += [ln1, ln2, qn, kn, wqkv, wo, wgu, wd]
             lw.ln1_w, lw.ln2_w, lw.q_norm_w, lw.k_norm_w = ln1.data_ptr(), ln2.data_ptr(), qn.data_ptr(), kn.data_ptr()
             lw.wqkv, lw.wo, lw.w_gate_up, lw.w_down = wqkv.data_ptr(), wo.data_ptr(), wgu.data_ptr(), wd.data_ptr()
@@ -119,6 +120,7 @@ class LlmRunner:
         w = LlmWeights()
         w.D, w.I, w.n_layers, w.Hq, w.Hkv, w.head_dim = D, I, L, Hq, Hkv, hd
         w.eps = c["rms_norm_eps"]
+        w.w_tiled = 1
         w.final_norm_w = fn.data_ptr()
         self._layers = layers
         w.layers = C.cast(layers, C.POINTER(LlmLayer))

@@ -55,12 +55,16 @@ def gemm(
 ) -> torch.Tensor:
     """``epilogue(a @ w.T)`` — a [M,K] bf16, w [N,K] bf16 (nn.Linear layout); see ``bd_gemm_bf16``."""
     lib = _lib.load()
-    require_cuda(a, w, bias, gate, res, out)
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
-    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
-    assert a.stride(1) == 1 and w.stride(1) == 1
+    tiled = isinstance(w, PackedWeight)
+    require_cuda(a, w.data if tiled else w, bias, gate, res, out)
+    assert a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1
     M, K = a.shape
-    N = w.shape[0]
+    if tiled:
+        assert w.K == K
+        N, ldw = w.N, 0
+    else:
+        assert w.dtype == torch.bfloat16 and w.dim() == 2 and a.shape[1] == w.shape[1] and w.stride(1) == 1
+        N, ldw = w.shape[0], w.stride(0)
     n_out = N // 2 if swiglu else N
     if out is None:
         out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
@@ -90,11 +94,40 @@ def gemm(
     ws_bytes = lib.bd_gemm_workspace_bytes(M, N, K, bn, splits)
     ws = (workspace or default_workspace(a.device)).get(ws_bytes)
     st = lib.bd_gemm_bf16(
-        ptr(a), C.c_int64(a.stride(0)), ptr(w), C.c_int64(w.stride(0)), M, N, K, C.byref(epi), ptr(ws),
-        C.c_size_t(ws.numel() if ws is not None else 0), bn, splits, 1 if pdl else 0, stream_ptr(),
+        ptr(a), C.c_int64(a.stride(0)), C.c_void_p(w.data_ptr()), C.c_int64(ldw), M, N, K, C.byref(epi), ptr(ws),
+        C.c_size_t(ws.numel() if ws is not None else 0), bn, splits, (1 if pdl else 0) | (2 if tiled else 0), stream_ptr(),
     )
     check(st, "bd_gemm_bf16")
     return out
+
+
+class PackedWeight:
+    """A Linear weight in the tile-major HBM layout of ``bd_pack_weight_tiles`` (+ its logical [N, K])."""
+
+    __slots__ = ("data", "N", "K")
+
+    def __init__(self, data: torch.Tensor, N: int, K: int):
+        self.data, self.N, self.K = data, N, K
+
+    def data_ptr(self):
+        return self.data.data_ptr()
+
+    @property
+    def device(self):
+        return self.data.device
+
+
+def pack_weight(w: torch.Tensor) -> PackedWeight:
+    """[N, K] bf16 row-major -> tile-major (one-time prepack; see ``bd_pack_weight_tiles``)."""
+    lib = _lib.load()
+    require_cuda(w)
+    assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
+    N, K = w.shape
+    lib.bd_packed_weight_elems.restype = C.c_size_t
+    n = lib.bd_packed_weight_elems(N, K)
+    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    check(lib.bd_pack_weight_tiles(ptr(w), C.c_int64(w.stride(0)), N, K, ptr(out), stream_ptr()), "bd_pack_weight_tiles")
+    return PackedWeight(out, N, K)
 
 
 def interleave16(gate_w: torch.Tensor, up_w: torch.Tensor, gate_b=None, up_b=None):

@@ -55,12 +55,13 @@ class T2IEngine:
         self.llm, self.head, self.ae = llm, head, ae
         self.device = torch.device(device)
         bf = lambda t: t.detach().to(self.device, torch.bfloat16).contiguous()
-        self.fc1_w, self.fc1_b, self.fc2_w, self.fc2_b = bf(fc1_w), bf(fc1_b), bf(fc2_w), bf(fc2_b)
+        self.fc1_w, self.fc1_b = ops.pack_weight(bf(fc1_w)), bf(fc1_b)
+        self.fc2_w, self.fc2_b = ops.pack_weight(bf(fc2_w)), bf(fc2_b)
         self.pn = parallel_num
         self.ps = int(parallel_num ** 0.5)
         self.vae_patch_size = vae_patch_size
         self.D = llm.cfg["hidden_size"]
-        self.zc = self.fc1_w.shape[1]
+        self.zc = self.fc1_w.K
         self.pos_1d = sincos_1d(self.D // 2, pe_max_len // vae_patch_size, self.device)
         self._pos_cache = {}
         self.timings = {}

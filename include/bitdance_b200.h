@@ -90,11 +90,18 @@ typedef struct {
  * modeling/utils.py:16-20). A, W bf16 row-major, lda/ldw multiples of 8 elements, 16-byte aligned bases.
  * fp32 accumulation on tcgen05 tensor cores; y = bf16(acc + bias) then the epilogue stages, each rounding to bf16.
  * bn: 0 = auto, else 64/128/256. splits: 0 = auto, else split-K factor (needs workspace >= splits*M*N*4 bytes).
- * flags: bit0 = launch with programmatic dependent launch. */
+ * flags: bit0 = launch with programmatic dependent launch; bit1 = W is tile-major (bd_pack_weight_tiles; ldw ignored). */
 int bd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                  const bd_gemm_epilogue_t* epi, void* workspace, size_t workspace_bytes, int bn, int splits,
                  int flags, bd_stream_t stream);
 size_t bd_gemm_workspace_bytes(int M, int N, int K, int bn, int splits);
+
+/* One-time weight re-layout for HBM streaming: W bf16 [N, K] row-major -> tile-major
+ * [ceil(N/128)][ceil(K/64)][128][64] (zero padded; bd_packed_weight_elems elements). A 128x64 tile is 16 KB CONTIGUOUS and
+ * the k-blocks of one 128-row slab are adjacent, so a CTA of the GEMM streams one contiguous HBM region instead of
+ * 128-byte pieces K*2 bytes apart (DRAM-page locality). */
+int bd_pack_weight_tiles(const void* W, int64_t ldw, int N, int K, void* out, bd_stream_t stream);
+size_t bd_packed_weight_elems(int N, int K);
 
 /* One-time weight re-layout for SwiGLU pairs: out rows [32j, 32j+16) = gate rows [16j, 16j+16),
  * out rows [32j+16, 32j+32) = up rows [16j, 16j+16). gate/up: bf16 [F, K] (F % 16 == 0); out: bf16 [2F, K].
@@ -141,6 +148,7 @@ typedef struct {
   int n_ada;    /* depth_adanln */
   int head_dim; /* 128 (modeling/) or 64 (imagenet_gen/) */
   int use_swiglu;
+  int w_tiled;     /* 1: every Linear weight below (except final_w) is in bd_pack_weight_tiles layout */
   int out_sigmoid; /* 1: 2*sigmoid(.)-1 (flow_head_parallel_x.py:341-342); 0: imagenet_gen diff_head_parallel.py:310 */
   const void *input_proj_w, *input_proj_b;
   const void *time0_w, *time0_b, *time2_w, *time2_b; /* time_embed.mlp.0 / .2 */
@@ -180,6 +188,7 @@ typedef struct {
 typedef struct {
   int D, I, n_layers, Hq, Hkv, head_dim;
   float eps;
+  int w_tiled;                  /* 1: wqkv / wo / w_gate_up / w_down are in bd_pack_weight_tiles layout */
   const void* final_norm_w;     /* bf16 [D] */
   const bd_llm_layer_t* layers; /* HOST array [n_layers] */
 } bd_llm_weights_t;

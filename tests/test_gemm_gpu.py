@@ -51,18 +51,22 @@ def check_close(out, ref, K, tag):
     (300, 640, 320, 128, 2),      # several M tiles + split
     (1024, 2048, 512, 256, 1),    # bs=8 rows
 ])
-def test_gemm_plain(M, N, K, bn, splits):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_gemm_plain(M, N, K, bn, splits, tiled):
     from bitdance_b200 import ops
     torch.manual_seed(0)
     a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
     bias = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16)
-    out = ops.gemm(a, w, bias=bias, bn=bn, splits=splits)
+    wk = ops.pack_weight(w) if tiled else w      # tile-major HBM layout (bd_pack_weight_tiles) or nn.Linear layout
+    out = ops.gemm(a, wk, bias=bias, bn=bn, splits=splits)
     torch.cuda.synchronize()
     check_close(out, ref_linear(a, w, bias), K, f"plain {M}x{N}x{K}")
-    out32 = ops.gemm(a, w, out_dtype=torch.float32, bn=bn, splits=splits)
+    out32 = ops.gemm(a, wk, out_dtype=torch.float32, bn=bn, splits=splits)
     torch.cuda.synchronize()
     check_close(out32, ref_linear(a, w, out_dtype=torch.float32), K, "f32 out")
+    if tiled and bn == 0:   # same tiles, same accumulation order: the two layouts must agree bit for bit
+        assert torch.equal(out, ops.gemm(a, w, bias=bias, bn=bn, splits=splits))
 
 
 @pytest.mark.parametrize("splits", [1, 3])
@@ -90,6 +94,7 @@ def test_gemm_epilogues(splits):
     bg, bu = bias[:F].contiguous(), bias[F:].contiguous()
     wi, bi = ops.interleave16(wg, wu, bg, bu)
     out = ops.gemm(a, wi, bias=bi, swiglu=True, splits=splits)
+    assert torch.equal(out, ops.gemm(a, ops.pack_weight(wi), bias=bi, swiglu=True, splits=splits))
     g = bf(a.float() @ wg.float().t() + bg.float())
     u = bf(a.float() @ wu.float().t() + bu.float())
     ref = bf(bf(torch.nn.functional.silu(g)) * u)
