@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--guidance", type=float, default=7.5)
     ap.add_argument("--ar-steps", type=int, default=None, help="debug only: truncate the AR loop (invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="replay the AR step as a CUDA graph (1) or launch it eagerly (0)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -207,6 +208,7 @@ def main():
     lib.bd_launch_count.restype = __import__("ctypes").c_ulonglong
     _lib.check(lib.bd_device_check(), "bd_device_check")
     eng, embed = build_synthetic_engine(args.model, dev, seed=rank)
+    eng.use_graph = bool(args.graph)
     m = MODELS[args.model]
     pn, vps = m["parallel_num"], eng.vae_patch_size
     h, w = args.height // vps, args.width // vps
@@ -307,7 +309,7 @@ def main():
                                f"CFG {args.guidance}, S={S} (+1), synthetic 64-token prompt",
                    "parallelism": f"replicas x{world} (independent images per GPU, no data-path collective)",
                    "l2": "inputs >> L2: 33 GB of bf16 weights streamed per AR step",
-                   "ms_per_ar_step": ms_ar, "prefill_ms": 1e3 * phases.get("prefill_s", 0.0),
+                   "cuda_graph": bool(args.graph), "ms_per_ar_step": ms_ar, "prefill_ms": 1e3 * phases.get("prefill_s", 0.0),
                    "truncated_ar_steps": args.ar_steps},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(ids_host.numel() * 8),

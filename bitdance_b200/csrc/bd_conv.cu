@@ -113,7 +113,7 @@ int bd_conv2d_nhwc(const void* x, const void* w_packed, const void* bias, const 
       BD_CUDA_TRY(cudaFuncSetAttribute(bd_conv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       set = true;
     }
-    LaunchCfg lc(grid, dim3(kGemmThreads), smem, stream, pdl);
+    LaunchCfg lc(grid, dim3(kConvThreads), smem, stream, pdl);
     BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, bd_conv_kernel<128>, ta, tw, g, epi));
   } else {
     static bool set = false;
@@ -122,7 +122,7 @@ int bd_conv2d_nhwc(const void* x, const void* w_packed, const void* bias, const 
       BD_CUDA_TRY(cudaFuncSetAttribute(bd_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       set = true;
     }
-    LaunchCfg lc(grid, dim3(kGemmThreads), smem, stream, pdl);
+    LaunchCfg lc(grid, dim3(kConvThreads), smem, stream, pdl);
     BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, bd_conv_kernel<64>, ta, tw, g, epi));
   }
   return BD_OK;

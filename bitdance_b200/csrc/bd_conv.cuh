@@ -33,7 +33,7 @@ constexpr int kConvStageBytes = (128 + kConvBN) * 64 * 2;
 constexpr int kConvSmemBytes = kConvStages * kConvStageBytes + 1024 + 256;
 
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 2)
 bd_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, ConvGeom g,
                GemmEpi epi) {
   constexpr int kABytes = 128 * 64 * 2;

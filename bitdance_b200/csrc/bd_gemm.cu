@@ -91,7 +91,7 @@ size_t gemm_workspace_bytes(int M, int N, int K, int bn, int splits) {
 
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const GemmEpi& epi,
               void* workspace, size_t workspace_bytes, int bn, int splits, bool pdl, cudaStream_t stream,
-              bool w_tiled) {
+              bool w_tiled, int* partial_splits) {
   BD_REQUIRE(A && W && epi.out);
   if (w_tiled) ldw = ((K + 63) / 64) * 64;
   BD_REQUIRE(M > 0 && N > 0 && K > 0);
@@ -126,6 +126,10 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
     default: rc = launch_gemm<256>(ta, tw, M, N, K, p.splits, partial, epi, pdl, stream, wt); break;
   }
   if (rc != BD_OK) return rc;
+  if (partial_splits) {
+    *partial_splits = p.splits;
+    return BD_OK;
+  }
   if (p.splits > 1) {
     const long long work = static_cast<long long>(M) * ((N + 31) / 32);
     dim3 grid(static_cast<unsigned>((work + 255) / 256));

@@ -48,19 +48,88 @@ __device__ __forceinline__ void epi_apply_store(const GemmEpi& e, const float (&
     return;
   }
   float y[32];
+  const long long mr = e.res_mod > 0 ? (m % e.res_mod) : m;
+  const bool fullc = (n0 + 32 <= N);
+  // vector-load the per-column operands of a full chunk (32 contiguous columns) when 16-byte aligned
+  float bv[32], gv[32], rv[32];
+  bool have_b = false, have_g = false, have_r = false;
+  if (fullc) {
+    if (e.bias && ((reinterpret_cast<uintptr_t>(e.bias + n0) & 15) == 0)) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 raw = reinterpret_cast<const uint4*>(e.bias + n0)[q];
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(p2[t]);
+          bv[8 * q + 2 * t] = f.x;
+          bv[8 * q + 2 * t + 1] = f.y;
+        }
+      }
+      have_b = true;
+    }
+    if (e.gate) {
+      const __nv_bfloat16* gp = e.gate + static_cast<long long>(m) * e.ld_gate + n0;
+      if ((reinterpret_cast<uintptr_t>(gp) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 raw = reinterpret_cast<const uint4*>(gp)[q];
+          const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(p2[t]);
+            gv[8 * q + 2 * t] = f.x;
+            gv[8 * q + 2 * t + 1] = f.y;
+          }
+        }
+        have_g = true;
+      }
+    }
+    if (e.res) {
+      if (e.res_f32) {
+        const float* rp = reinterpret_cast<const float*>(e.res) + mr * e.ld_res + n0;
+        if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 f = reinterpret_cast<const float4*>(rp)[q];
+            rv[4 * q] = f.x; rv[4 * q + 1] = f.y; rv[4 * q + 2] = f.z; rv[4 * q + 3] = f.w;
+          }
+          have_r = true;
+        }
+      } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(e.res) + mr * e.ld_res + n0;
+        if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 raw = reinterpret_cast<const uint4*>(rp)[q];
+            const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(p2[t]);
+              rv[8 * q + 2 * t] = f.x;
+              rv[8 * q + 2 * t + 1] = f.y;
+            }
+          }
+          have_r = true;
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float v = acc[j];
     const int n = n0 + j;
     const bool ok = n < N;
-    if (e.bias && ok) v += __bfloat162float(e.bias[n]);
+    if (e.bias && ok) v += have_b ? bv[j] : __bfloat162float(e.bias[n]);
     v = bf16_round(v);
     if (e.act == kActSilu) v = bf16_round(siluf_(v));
     if (e.act == kActGeluTanh) v = bf16_round(gelu_tanhf_(v));
-    if (e.gate && ok) v = bf16_round(v * __bfloat162float(e.gate[static_cast<long long>(m) * e.ld_gate + n]));
+    if (e.gate && ok)
+      v = bf16_round(v * (have_g ? gv[j] : __bfloat162float(e.gate[static_cast<long long>(m) * e.ld_gate + n])));
     if (e.res && ok) {
-      const long long mr = e.res_mod > 0 ? (m % e.res_mod) : m;
-      if (e.res_f32)
+      if (have_r)
+        v += rv[j];
+      else if (e.res_f32)
         v += reinterpret_cast<const float*>(e.res)[mr * e.ld_res + n];
       else
         v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.res)[mr * e.ld_res + n]);
@@ -95,15 +164,20 @@ __device__ __forceinline__ void epi_apply_store(const GemmEpi& e, const float (&
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 224;  // warp0 W producer, warp1 MMA issuer (+TMEM alloc), warp2 A producer, warps3-6 epilogue
+constexpr int kConvThreads = 192;  // bd_conv.cuh keeps the single-producer layout
 
+// Shared-memory plan (1 CTA per SM, ~224 KB): the W (weights, from HBM) and A (activations, L2-resident) operands have
+// SEPARATE rings with their own producer warps. HBM latency under load is ~2-3 us, so what bounds a weight-streaming CTA
+// is the number of W bytes it keeps in flight: the W ring takes 160 KB (10 x 16 KB tiles at BN=128), A gets 4 stages.
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
   static constexpr int kWBytes = BN * kGemmBK * 2;
-  static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kAStages = 4;
+  static constexpr int kWStages = (160 * 1024) / kWBytes;  // 5 / 10 / 20 for BN = 256 / 128 / 64
+  static constexpr int kBarBytes = (2 * kAStages + 2 * kWStages + 1) * 8 + 16;
+  static constexpr int kSmemBytes = kAStages * kABytes + kWStages * kWBytes + 1024 /*align slack*/ + kBarBytes;
   static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
 };
 
@@ -114,9 +188,13 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* acc_bar = empty_bar + Cfg::kStages;
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + Cfg::kWStages * Cfg::kWBytes;
+  uint64_t* full_w = reinterpret_cast<uint64_t*>(smem_a + Cfg::kAStages * Cfg::kABytes);
+  uint64_t* empty_w = full_w + Cfg::kWStages;
+  uint64_t* full_a = empty_w + Cfg::kWStages;
+  uint64_t* empty_a = full_a + Cfg::kAStages;
+  uint64_t* acc_bar = empty_a + Cfg::kAStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -128,15 +206,19 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int nkb = kb_end - kb_begin;
 
   if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < Cfg::kWStages; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&empty_w[s], 1);
+    }
+    for (int s = 0; s < Cfg::kAStages; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&empty_a[s], 1);
     }
     mbar_init(acc_bar, 1);
     fence_mbar_init();
   }
+  if (warp == 2 && elect_one()) tma_prefetch_desc(&tmap_a);
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -146,42 +228,40 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // Let the next kernel in the stream begin its own prologue / weight prefetch as SMs free up.
   grid_dep_launch();
 
-  // W tile of k-block kb into stage memory. Row-major W: one strided box (BN rows x 128 B, rows K*2 bytes apart).
-  // Tile-major W (bd_pack_weight_tiles: [n_tile][k_block][128][64], every 128x64 tile = 16 KB CONTIGUOUS in HBM, the
-  // k-blocks of one n_tile adjacent): each CTA streams one contiguous region — DRAM-page friendly.
-  auto load_w = [&](uint8_t* dst, uint64_t* bar, int kb) {
-    if (!w_tiled) {
-      tma_load_2d(dst, &tmap_w, bar, kb * kGemmBK, n0, kEvictFirst);
-    } else if (BN >= 128) {
-#pragma unroll
-      for (int hh = 0; hh < BN / 128; ++hh)
-        tma_load_2d(dst + hh * (128 * kGemmBK * 2), &tmap_w, bar, 0, ((n0 / 128 + hh) * num_kb + kb) * 128, kEvictFirst);
-    } else {
-      tma_load_2d(dst, &tmap_w, bar, 0, ((n0 / 128) * num_kb + kb) * 128 + (n0 % 128), kEvictFirst);
-    }
-  };
-
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== W producer: weights never depend on the upstream kernel -> no griddepcontrol.wait =====
+    // Row-major W: one strided box (BN rows x 128 B, rows K*2 bytes apart). Tile-major W (bd_pack_weight_tiles:
+    // [n_tile][k_block][128][64], every 128x64 tile = 16 KB CONTIGUOUS in HBM, the k-blocks of one n_tile adjacent):
+    // each CTA streams one contiguous region — DRAM-page friendly.
+    if (elect_one()) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::kWStages;
+        if (i >= Cfg::kWStages) mbar_wait(&empty_w[s], (static_cast<uint32_t>(i / Cfg::kWStages) & 1u) ^ 1u);
+        mbar_expect_tx(&full_w[s], Cfg::kWBytes);
+        uint8_t* dst = smem_w + s * Cfg::kWBytes;
+        const int kb = kb_begin + i;
+        if (!w_tiled) {
+          tma_load_2d(dst, &tmap_w, &full_w[s], kb * kGemmBK, n0, kEvictFirst);
+        } else if (BN >= 128) {
+#pragma unroll
+          for (int hh = 0; hh < (BN >= 128 ? BN / 128 : 1); ++hh)
+            tma_load_2d(dst + hh * (128 * kGemmBK * 2), &tmap_w, &full_w[s], 0, ((n0 / 128 + hh) * num_kb + kb) * 128,
+                        kEvictFirst);
+        } else {
+          tma_load_2d(dst, &tmap_w, &full_w[s], 0, ((n0 / 128) * num_kb + kb) * 128 + (n0 % 128), kEvictFirst);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== A producer: activations come from the upstream kernel =====================
     if (elect_one()) {
       const uint64_t a_hint = a_hint_last ? kEvictLast : kEvictNormal;
-      // Phase 1: weights only (independent of the upstream kernel) for the first ring of stages.
-      const int pre = nkb < Cfg::kStages ? nkb : Cfg::kStages;
-      for (int i = 0; i < pre; ++i) {
-        mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
-        load_w(smem + i * Cfg::kStageBytes + Cfg::kABytes, &full_bar[i], kb_begin + i);
-      }
-      grid_dep_wait();  // activations are produced by the upstream kernel
-      for (int i = 0; i < pre; ++i)
-        tma_load_2d(smem + i * Cfg::kStageBytes, &tmap_a, &full_bar[i], (kb_begin + i) * kGemmBK, m0, a_hint);
-      // Phase 2: steady state.
-      for (int i = pre; i < nkb; ++i) {
-        const int s = i % Cfg::kStages;
-        const uint32_t ph = static_cast<uint32_t>(i / Cfg::kStages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        load_w(smem + s * Cfg::kStageBytes + Cfg::kABytes, &full_bar[s], kb_begin + i);
-        tma_load_2d(smem + s * Cfg::kStageBytes, &tmap_a, &full_bar[s], (kb_begin + i) * kGemmBK, m0, a_hint);
+      grid_dep_wait();
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::kAStages;
+        if (i >= Cfg::kAStages) mbar_wait(&empty_a[s], (static_cast<uint32_t>(i / Cfg::kAStages) & 1u) ^ 1u);
+        mbar_expect_tx(&full_a[s], Cfg::kABytes);
+        tma_load_2d(smem_a + s * Cfg::kABytes, &tmap_a, &full_a[s], (kb_begin + i) * kGemmBK, m0, a_hint);
       }
     }
   } else if (warp == 1) {
@@ -189,24 +269,25 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % Cfg::kStages;
-        const uint32_t ph = static_cast<uint32_t>(i / Cfg::kStages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+        const int sw = i % Cfg::kWStages, sa = i % Cfg::kAStages;
+        mbar_wait(&full_w[sw], static_cast<uint32_t>(i / Cfg::kWStages) & 1u);
+        mbar_wait(&full_a[sa], static_cast<uint32_t>(i / Cfg::kAStages) & 1u);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t w_addr = a_addr + Cfg::kABytes;
+        const uint32_t a_addr = smem_u32(smem_a + sa * Cfg::kABytes);
+        const uint32_t w_addr = smem_u32(smem_w + sw * Cfg::kWBytes);
 #pragma unroll
         for (int k = 0; k < kGemmBK / 16; ++k) {
           const uint64_t ad = umma_desc_k_sw128(a_addr + k * 32);
           const uint64_t wd = umma_desc_k_sw128(w_addr + k * 32);
           umma_bf16(tmem_base, ad, wd, idesc, (i | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        umma_commit(&empty_w[sw]);  // frees the stages once these MMAs retire
+        umma_commit(&empty_a[sa]);
       }
       umma_commit(acc_bar);  // accumulator complete
     }
   } else {
-    // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
+    // ===================== epilogue: warps 3..6, TMEM lane quarter = warp % 4 =====================
     const int q = warp & 3;
     const int m = m0 + q * 32 + static_cast<int>(lane_id());
     grid_dep_wait();  // res / gate come from upstream kernels; out may still be read by them

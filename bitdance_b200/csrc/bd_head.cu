@@ -11,6 +11,7 @@
 // Noise is an input (drawn by torch in the reference's call order), so the sampler itself is deterministic.
 #include "bd_host.h"
 #include "bd_ptx.cuh"
+#include "bd_rowops.cuh"
 
 namespace bd {
 
@@ -159,61 +160,56 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_mod_kernel(
   }
 }
 
-// FinalLayer (flow_head_parallel_x.py:169-173) + output map (:341-342), one CTA per token row:
-//   h = bf16(LN(x) * bf16(1+scale) + shift);  o_c = bf16(sum_d h_d W[c,d] + bias_c);
-//   pred_c = out_sigmoid ? bf16(bf16(2 * bf16(sigmoid(o_c))) - 1) : o_c          -> fp32 [M, C]
-__global__ void __launch_bounds__(256) head_final_kernel(const __nv_bfloat16* __restrict__ x, int D,
-                                                         const __nv_bfloat16* __restrict__ scale,
-                                                         const __nv_bfloat16* __restrict__ shift, long long ld_mod,
-                                                         const __nv_bfloat16* __restrict__ Wf,
-                                                         const __nv_bfloat16* __restrict__ bf, int C, int out_sigmoid,
-                                                         float eps, float* __restrict__ pred) {
+// FinalLayer.linear + output map on an already LN-modulated row a (bf16 [M, D]); one CTA per token row:
+//   o_c = bf16(sum_d a_d W[c,d] + bias_c);  pred_c = out_sigmoid ? bf16(bf16(2 * bf16(sigmoid(o_c))) - 1) : o_c
+// 8 warps x 4 channels each; every lane keeps 4 independent 16-byte weight loads in flight per iteration.
+__global__ void __launch_bounds__(256) head_out_kernel(const __nv_bfloat16* __restrict__ a, int D,
+                                                       const __nv_bfloat16* __restrict__ Wf,
+                                                       const __nv_bfloat16* __restrict__ bfin, int C, int out_sigmoid,
+                                                       float* __restrict__ pred) {
   extern __shared__ float hrow[];  // [D]
-  __shared__ float red[32];
   grid_dep_launch();
   grid_dep_wait();
-  const int m = blockIdx.x;
-  float sum = 0.f;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const float f = __bfloat162float(x[static_cast<long long>(m) * D + d]);
-    hrow[d] = f;
-    sum += f;
-  }
-  const float mean = block_sum(sum, red) / static_cast<float>(D);
-  float sq = 0.f;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const float t = hrow[d] - mean;
-    sq += t * t;
-  }
-  const float rstd = rsqrtf(block_sum(sq, red) / static_cast<float>(D) + eps);
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const float one_plus = bf16_round(1.0f + __bfloat162float(scale[m * ld_mod + d]));
-    hrow[d] = bf16_round((hrow[d] - mean) * rstd * one_plus + __bfloat162float(shift[m * ld_mod + d]));
+  const long long m = blockIdx.x;
+  for (int c8 = threadIdx.x; c8 < D / 8; c8 += blockDim.x) {
+    float v[8];
+    load_bf16x8(a + m * D + c8 * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hrow[c8 * 8 + j] = v[j];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = warp; c < C; c += (blockDim.x >> 5)) {
-    const __nv_bfloat16* wr = Wf + static_cast<long long>(c) * D;
-    float acc = 0.f;
+  for (int c0 = warp * 4; c0 < C; c0 += 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int d = lane * 8; d < D; d += 256) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(wr + d);
-      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      uint4 raw[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(p[j]);
-        acc = fmaf(hrow[d + 2 * j], f.x, acc);
-        acc = fmaf(hrow[d + 2 * j + 1], f.y, acc);
+      for (int u = 0; u < 4; ++u)
+        raw[u] = (c0 + u < C) ? *reinterpret_cast<const uint4*>(Wf + static_cast<long long>(c0 + u) * D + d)
+                              : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(p2[j]);
+          acc[u] = fmaf(hrow[d + 2 * j], f.x, acc[u]);
+          acc[u] = fmaf(hrow[d + 2 * j + 1], f.y, acc[u]);
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      float o = bf16_round(acc + (bf ? __bfloat162float(bf[c]) : 0.f));
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+    if (lane < 4 && c0 + lane < C) {
+      float o = bf16_round(acc[lane] + (bfin ? __bfloat162float(bfin[c0 + lane]) : 0.f));
       if (out_sigmoid) {
-        const float s = bf16_round(1.0f / (1.0f + expf(-o)));
-        o = bf16_round(bf16_round(2.0f * s) - 1.0f);
+        const float sg = bf16_round(1.0f / (1.0f + expf(-o)));
+        o = bf16_round(bf16_round(2.0f * sg) - 1.0f);
       }
-      pred[static_cast<long long>(m) * C + c] = o;
+      pred[m * C + c0 + lane] = o;
     }
   }
 }
@@ -227,7 +223,7 @@ struct SdeStep {
   int last;
 };
 __global__ void sde_step_kernel(float* __restrict__ x, const float* __restrict__ pred, const float* __restrict__ noise,
-                                int n, SdeStep s, __nv_bfloat16* __restrict__ xb) {
+                                int n, SdeStep s, __nv_bfloat16* __restrict__ xb, int C, int Cp) {
   grid_dep_launch();
   grid_dep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,16 +243,17 @@ __global__ void sde_step_kernel(float* __restrict__ x, const float* __restrict__
     xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(drift, s.dt)), __fmul_rn(s.noise_scale, noise[i]));
   }
   x[i] = xn;
-  if (xb) {
+  if (xb) {  // xb rows are padded to Cp columns (zeros beyond C): the input_proj GEMM reads full 128-byte k-blocks
     const __nv_bfloat16 b = __float2bfloat16_rn(xn);
-    xb[i] = b;
-    if (s.cfg_mult == 2) xb[n + i] = b;
+    const int r = i / C, c = i % C, rows = n / C;
+    xb[static_cast<long long>(r) * Cp + c] = b;
+    if (s.cfg_mult == 2) xb[static_cast<long long>(rows + r) * Cp + c] = b;
   }
 }
 
 // x0 = noise[0]; xb = bf16(cat[x0] * mult)
 __global__ void sde_init_kernel(float* __restrict__ x, const float* __restrict__ noise0, int n, int cfg_mult,
-                                __nv_bfloat16* __restrict__ xb) {
+                                __nv_bfloat16* __restrict__ xb, int C, int Cp) {
   grid_dep_launch();
   grid_dep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,8 +261,9 @@ __global__ void sde_init_kernel(float* __restrict__ x, const float* __restrict__
   const float v = noise0[i];
   x[i] = v;
   const __nv_bfloat16 b = __float2bfloat16_rn(v);
-  xb[i] = b;
-  if (cfg_mult == 2) xb[n + i] = b;
+  const int r = i / C, c = i % C, rows = n / C;
+  xb[static_cast<long long>(r) * Cp + c] = b;
+  if (cfg_mult == 2) xb[static_cast<long long>(rows + r) * Cp + c] = b;
 }
 
 template <typename... KArgs, typename... Args>
@@ -293,7 +291,7 @@ static HeadWs head_ws_layout(const bd_head_weights_t& w, int M, int n_rows_x, in
   const size_t D = w.D, C = w.C;
   const int n_mod = w.n_ada * 6 * w.D + 2 * w.D;
   const size_t wide = 3 * D > static_cast<size_t>(2 * w.hidden) ? 3 * D : 2 * w.hidden;
-  L.xb = take(static_cast<size_t>(M) * C * 2);
+  L.xb = take(static_cast<size_t>(M) * ((C + 63) / 64 * 64) * 2);
   L.h = take(M * D * 2);
   L.a = take(M * D * 2);
   L.o = take(M * D * 2);
@@ -352,7 +350,7 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
   BD_REQUIRE(wp && cond && noise && sched_host && x_out && workspace);
   const bd_head_weights_t& w = *wp;
   BD_REQUIRE(B > 0 && pn > 0 && (cfg_mult == 1 || cfg_mult == 2) && S >= 0);
-  BD_REQUIRE(w.D > 0 && (w.D % 64) == 0 && w.D <= 8192 && w.C > 0 && (w.C % 8) == 0 && w.Dz > 0 && (w.Dz % 8) == 0);
+  BD_REQUIRE(w.D > 0 && (w.D % 64) == 0 && w.D <= 6144 && w.C > 0 && (w.C % 8) == 0 && w.Dz > 0 && (w.Dz % 8) == 0);
   BD_REQUIRE(w.n_blocks > 0 && w.n_blocks <= BD_HEAD_MAX_BLOCKS && w.n_ada > 0 && (w.n_blocks % w.n_ada) == 0);
   BD_REQUIRE(w.head_dim == 64 || w.head_dim == 128);
   BD_REQUIRE(pn <= 64);  // one KV tile per block of parallel tokens
@@ -412,7 +410,9 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
     BD_TRY(gemm(condb, w.Dz, w.cond_w, M, D, w.Dz, e));
   }
   const int nel = nx * C;
-  BD_TRY(launch(sde_init_kernel, dim3((nel + 255) / 256), dim3(256), 0, st, pdl, x, noise, nel, cfg_mult, xb));
+  const int Cp = (C + 63) / 64 * 64;
+  BD_CUDA_TRY(cudaMemsetAsync(xb, 0, static_cast<size_t>(M) * Cp * 2, st));
+  BD_TRY(launch(sde_init_kernel, dim3((nel + 255) / 256), dim3(256), 0, st, false, x, noise, nel, cfg_mult, xb, C, Cp));
 
   // ---- S stochastic evaluations + 1 deterministic ----
   for (int it = 0; it <= S; ++it) {
@@ -422,7 +422,8 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
       e.bias = bf(w.input_proj_b);
       e.out = h;
       e.ld_out = D;
-      BD_TRY(gemm(xb, C, w.input_proj_w, M, D, C, e));
+      // tile-major input_proj weights are zero-padded to 64 columns, so K can be the padded width
+      BD_TRY(gemm(xb, Cp, w.input_proj_w, M, D, w.w_tiled ? Cp : C, e));
     }
     {  // y = silu(t_emb + c_emb)
       const long long n = static_cast<long long>(M) * D / 8;
@@ -436,12 +437,15 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
       e.ld_out = n_mod;
       BD_TRY(gemm(y, D, w.ada_w, M, n_mod, D, e));
     }
+    const __nv_bfloat16* mf = mod + static_cast<long long>(w.n_ada) * 6 * D;  // final scale | shift
+    // a = norm1_0(h) * (1 + scale1) + shift1 for the first block (h comes straight from input_proj)
+    BD_TRY(launch(layernorm_mod_kernel, dim3(M), dim3(kLnThreads), 0, st, pdl, (const __nv_bfloat16*)h, (long long)D,
+                  w.blocks[0].norm1_w, w.blocks[0].norm1_b, (const __nv_bfloat16*)mod, (const __nv_bfloat16*)(mod + D),
+                  (long long)n_mod, a, (long long)D, D, 1e-6f));
     for (int blk = 0; blk < w.n_blocks; ++blk) {
       const bd_head_block_t& bw = w.blocks[blk];
       const __nv_bfloat16* md = mod + static_cast<long long>(blk / switch_freq) * 6 * D;
       // chunk order: scale1, shift1, gate1, scale2, shift2, gate2
-      BD_TRY(launch(layernorm_mod_kernel, dim3(M), dim3(kLnThreads), 0, st, pdl, (const __nv_bfloat16*)h,
-                    (long long)D, bw.norm1_w, bw.norm1_b, md, md + D, (long long)n_mod, a, (long long)D, D, 1e-6f));
       {
         GemmEpi e;
         e.bias = bf(bw.wqkv_b);
@@ -450,20 +454,43 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
         BD_TRY(gemm(a, D, bw.wqkv_w, M, 3 * D, D, e));
       }
       BD_TRY(attn_run_head(qkv, o, R, pn, D, w.head_dim, pdl, st));
-      {  // h = h + (wo(o) + b) * gate1
+      // h = h + (wo(o) + b) * gate1 ; a = norm2(h) * (1 + scale2) + shift2
+      // When K is split the reduction, this epilogue and the following LayerNorm-modulate run in ONE row kernel.
+      auto gated_res_then_norm = [&](const void* A_, long long lda, const void* W_, int Kdim, const void* bias_,
+                                     const __nv_bfloat16* gate_, const float* nw, const float* nb,
+                                     const __nv_bfloat16* sc, const __nv_bfloat16* sh) -> int {
         GemmEpi e;
-        e.bias = bf(bw.wo_b);
-        e.gate = md + 2 * D;
+        e.bias = bf(bias_);
+        e.gate = gate_;
         e.ld_gate = n_mod;
         e.res = h;
         e.ld_res = D;
         e.out = h;
         e.ld_out = D;
-        BD_TRY(gemm(o, D, bw.wo_w, M, D, D, e));
-      }
-      BD_TRY(launch(layernorm_mod_kernel, dim3(M), dim3(kLnThreads), 0, st, pdl, (const __nv_bfloat16*)h,
-                    (long long)D, bw.norm2_w, bw.norm2_b, md + 3 * D, md + 4 * D, (long long)n_mod, a, (long long)D, D,
-                    1e-6f));
+        int S_used = 1;
+        BD_TRY(gemm_bf16(A_, lda, W_, Kdim, M, D, Kdim, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0, &S_used));
+        if (S_used > 1) {
+          HeadRowArgs ra;
+          ra.partial = static_cast<const float*>(gws);
+          ra.splits = S_used;
+          ra.M = M;
+          ra.D = D;
+          ra.bias = bf(bias_);
+          ra.gate = gate_;
+          ra.h = h;
+          ra.ln_w = nw;
+          ra.ln_b = nb;
+          ra.scale = sc;
+          ra.shift = sh;
+          ra.ld_mod = n_mod;
+          ra.a = a;
+          ra.eps = 1e-6f;
+          return launch(head_splitk_row_kernel, dim3(M), dim3(kRowThreads), 0, st, pdl, ra);
+        }
+        return launch(layernorm_mod_kernel, dim3(M), dim3(kLnThreads), 0, st, pdl, (const __nv_bfloat16*)h, (long long)D,
+                      nw, nb, sc, sh, (long long)n_mod, a, (long long)D, D, 1e-6f);
+      };
+      BD_TRY(gated_res_then_norm(o, D, bw.wo_w, D, bw.wo_b, md + 2 * D, bw.norm2_w, bw.norm2_b, md + 3 * D, md + 4 * D));
       if (w.use_swiglu) {
         GemmEpi e;
         e.bias = bf(bw.w1_b);
@@ -479,23 +506,17 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
         e.ld_out = w.hidden;
         BD_TRY(gemm(a, D, bw.w1_w, M, w.hidden, D, e));
       }
-      {  // h = h + (w2(g) + b) * gate2
-        GemmEpi e;
-        e.bias = bf(bw.w2_b);
-        e.gate = md + 5 * D;
-        e.ld_gate = n_mod;
-        e.res = h;
-        e.ld_res = D;
-        e.out = h;
-        e.ld_out = D;
-        BD_TRY(gemm(g, w.hidden, bw.w2_w, M, D, w.hidden, e));
+      // h = h + (w2(g) + b) * gate2 ; a = the NEXT normalisation: next block's norm1-modulate, or the final layer's
+      if (blk + 1 < w.n_blocks) {
+        const bd_head_block_t& nb = w.blocks[blk + 1];
+        const __nv_bfloat16* mdn = mod + static_cast<long long>((blk + 1) / switch_freq) * 6 * D;
+        BD_TRY(gated_res_then_norm(g, w.hidden, bw.w2_w, w.hidden, bw.w2_b, md + 5 * D, nb.norm1_w, nb.norm1_b, mdn, mdn + D));
+      } else {
+        BD_TRY(gated_res_then_norm(g, w.hidden, bw.w2_w, w.hidden, bw.w2_b, md + 5 * D, nullptr, nullptr, mf, mf + D));
       }
     }
-    {
-      const __nv_bfloat16* mf = mod + static_cast<long long>(w.n_ada) * 6 * D;  // scale | shift
-      BD_TRY(launch(head_final_kernel, dim3(M), dim3(256), static_cast<size_t>(D) * 4, st, pdl, (const __nv_bfloat16*)h,
-                    D, mf, mf + D, (long long)n_mod, bf(w.final_w), bf(w.final_b), C, w.out_sigmoid, 1e-6f, pred));
-    }
+    BD_TRY(launch(head_out_kernel, dim3(M), dim3(256), static_cast<size_t>(D) * 4, st, pdl, (const __nv_bfloat16*)a, D,
+                  bf(w.final_w), bf(w.final_b), C, w.out_sigmoid, pred));
     if (trace)
       BD_CUDA_TRY(cudaMemcpyAsync(trace + static_cast<long long>(it) * M * C, pred, sizeof(float) * M * C,
                                   cudaMemcpyDeviceToDevice, st));
@@ -511,7 +532,7 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
     s.last = (it == S) ? 1 : 0;
     const float* nz = (it < S) ? noise + static_cast<long long>(it + 1) * nel : noise;
     BD_TRY(launch(sde_step_kernel, dim3((nel + 255) / 256), dim3(256), 0, st, pdl, x, (const float*)pred, nz, nel, s,
-                  (it < S) ? xb : (__nv_bfloat16*)nullptr));
+                  (it < S) ? xb : (__nv_bfloat16*)nullptr, C, Cp));
   }
   BD_CUDA_TRY(cudaMemcpyAsync(x_out, x, sizeof(float) * nel, cudaMemcpyDeviceToDevice, st));
   return BD_OK;

@@ -62,9 +62,12 @@ struct GemmEpi {
 // Internal C++ entry points shared by the composite ops (bd_head.cu, bd_llm.cu, ...).
 size_t gemm_workspace_bytes(int M, int N, int K, int bn, int splits);
 // w_tiled: W is in the tile-major layout of bd_pack_weight_tiles (ldw ignored).
+// partial_splits != nullptr: when the plan splits K, ONLY the partial-sum GEMM is launched (fp32 partials
+// [S][M][N] at the start of `workspace`), *partial_splits = S and the caller runs its own fused reduction; when the
+// plan does not split, the epilogue runs inside the GEMM as usual and *partial_splits = 1.
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const GemmEpi& epi,
               void* workspace, size_t workspace_bytes, int bn, int splits, bool pdl, cudaStream_t stream,
-              bool w_tiled = false);
+              bool w_tiled = false, int* partial_splits = nullptr);
 
 int num_sms();
 

@@ -11,6 +11,7 @@
 // Rounding policy: oracle/llm.py (stream_f32 = AR steps, else prefill).
 #include "bd_host.h"
 #include "bd_ptx.cuh"
+#include "bd_rowops.cuh"
 
 namespace bd {
 
@@ -237,7 +238,7 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
   const bd_llm_weights_t& w = *wp;
   BD_REQUIRE(R > 0 && S > 0 && w.n_layers > 0 && w.layers);
   BD_REQUIRE(w.head_dim == 128 || w.head_dim == 64);
-  BD_REQUIRE((w.D % 64) == 0 && (w.I % 64) == 0 && (w.Hq % w.Hkv) == 0);
+  BD_REQUIRE((w.D % 64) == 0 && w.D <= 6144 && (w.I % 64) == 0 && (w.Hq % w.Hkv) == 0);
   BD_REQUIRE(attn_splits >= 1 && sk_bound >= S && max_pages * 64 >= sk_bound);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const bool pdl = (flags & 1) != 0;
@@ -263,11 +264,40 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
                     D, w.eps, (const float*)nullptr, 1);
   };
 
+  // residual add of a projection + the RMSNorm that follows it. When K is split, the reduction of the fp32 partials,
+  // the residual add and the norm run in ONE row kernel; otherwise the GEMM epilogue adds the residual and the
+  // stand-alone norm kernel follows. next_norm == nullptr: no norm (last layer; the final norm has its own kernel).
+  auto proj_res_then_norm = [&](const void* A_, int Kdim, const void* W_, const void* next_norm) -> int {
+    GemmEpi e;
+    e.res = hidden;
+    e.ld_res = D;
+    e.res_f32 = stream_f32;
+    e.out = hidden;
+    e.ld_out = D;
+    e.out_f32 = stream_f32;
+    int S_used = 1;
+    BD_TRY(gemm_bf16(A_, Kdim, W_, Kdim, M, D, Kdim, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0, &S_used));
+    if (S_used > 1) {
+      LlmRowArgs ra;
+      ra.partial = static_cast<const float*>(gws);
+      ra.splits = S_used;
+      ra.M = M;
+      ra.D = D;
+      ra.hidden = hidden;
+      ra.stream_f32 = stream_f32;
+      ra.norm_w = bf(next_norm);
+      ra.a = a;
+      ra.eps = w.eps;
+      return launch_k(llm_splitk_row_kernel, dim3(M), dim3(kRowThreads), 0, st, pdl, ra);
+    }
+    return next_norm ? norm_to_bf16(next_norm) : BD_OK;
+  };
+
+  BD_TRY(norm_to_bf16(w.layers[0].ln1_w));
   for (int li = 0; li < w.n_layers; ++li) {
     const bd_llm_layer_t& lw = w.layers[li];
     __nv_bfloat16* kpool = reinterpret_cast<__nv_bfloat16*>(kv_pool) + static_cast<long long>(li) * kv_layer_stride;
     __nv_bfloat16* vpool = kpool + kv_v_offset;
-    BD_TRY(norm_to_bf16(lw.ln1_w));
     {
       GemmEpi e;
       e.out = qkv;
@@ -302,17 +332,7 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
     // keys visible to block b: seq_lens[b] (past) + S (this block), read on the device by the attention kernel
     BD_TRY(attn_run_llm(q, kpool, vpool, page_table, max_pages, seq_lens, sk_bound, o, R, S, w.Hq, w.Hkv, hd, causal,
                         attn_splits, aws, aws_bytes, pdl, st));
-    {
-      GemmEpi e;
-      e.res = hidden;
-      e.ld_res = D;
-      e.res_f32 = stream_f32;
-      e.out = hidden;
-      e.ld_out = D;
-      e.out_f32 = stream_f32;
-      BD_TRY(gemm_bf16(o, w.Hq * hd, lw.wo, w.Hq * hd, M, D, w.Hq * hd, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0));
-    }
-    BD_TRY(norm_to_bf16(lw.ln2_w));
+    BD_TRY(proj_res_then_norm(o, w.Hq * hd, lw.wo, lw.ln2_w));
     {
       GemmEpi e;
       e.swiglu = 1;
@@ -320,16 +340,7 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
       e.ld_out = w.I;
       BD_TRY(gemm_bf16(a, D, lw.w_gate_up, D, M, 2 * w.I, D, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0));
     }
-    {
-      GemmEpi e;
-      e.res = hidden;
-      e.ld_res = D;
-      e.res_f32 = stream_f32;
-      e.out = hidden;
-      e.ld_out = D;
-      e.out_f32 = stream_f32;
-      BD_TRY(gemm_bf16(g, w.I, lw.w_down, w.I, M, D, w.I, e, gws, gws_bytes, 0, 0, pdl, st, w.w_tiled != 0));
-    }
+    BD_TRY(proj_res_then_norm(g, w.I, lw.w_down, li + 1 < w.n_layers ? w.layers[li + 1].ln1_w : nullptr));
   }
   if (stream_f32)
     BD_TRY(launch_k(rmsnorm_kernel<true, true>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden,

@@ -158,7 +158,8 @@ class LlmRunner:
         return s
 
     def forward(self, hidden: torch.Tensor, cache: KVCache, r0: int, R: int, *, causal: bool, out_add=None,
-                out_add_mod: int = 0, attn_splits: int | None = None, pdl: bool = True) -> torch.Tensor:
+                out_add_mod: int = 0, attn_splits: int | None = None, pdl: bool = True, sk_bound: int | None = None,
+                track_host: bool = True) -> torch.Tensor:
         """hidden: [R, S, D] fp32 (AR stream) or bf16 (prefill stream) for sequences r0..r0+R; OVERWRITTEN.
         Returns the final-norm output [R, S, D] in the stream dtype (+ out_add rows when given)."""
         lib = _lib.load()
@@ -166,7 +167,8 @@ class LlmRunner:
         S, D = hidden.shape[1], hidden.shape[2]
         stream_f32 = hidden.dtype == torch.float32
         assert stream_f32 or hidden.dtype == torch.bfloat16
-        sk_bound = max(cache.host_lens[r0:r0 + R]) + S
+        if sk_bound is None:
+            sk_bound = max(cache.host_lens[r0:r0 + R]) + S
         assert sk_bound <= cache.max_tokens, "KV cache capacity exceeded"
         if attn_splits is None:
             attn_splits = self.plan_splits(R, S, sk_bound)
@@ -186,6 +188,7 @@ class LlmRunner:
             ptr(out), ptr(out_add), out_add_mod, attn_splits, ptr(self._ws), C.c_size_t(self._ws.numel()),
             1 if pdl else 0, stream_ptr())
         check(st, "bd_llm_forward")
-        for r in range(r0, r0 + R):
-            cache.host_lens[r] += S
+        if track_host:
+            for r in range(r0, r0 + R):
+                cache.host_lens[r] += S
         return out

@@ -65,6 +65,19 @@ class T2IEngine:
         self.pos_1d = sincos_1d(self.D // 2, pe_max_len // vae_patch_size, self.device)
         self._pos_cache = {}
         self.timings = {}
+        self.use_graph = False
+        self._graph_state = {}
+        self._kv = {}
+
+    def _get_cache(self, R, max_len):
+        """KV pools are reused across calls (sized for the largest request so far); only the lengths are reset."""
+        c = self._kv.get(R)
+        if c is None or c.max_tokens < max_len:
+            c = self.llm.new_cache(R, max_len)
+            self._kv[R] = c
+        c.seq_lens.zero_()
+        c.host_lens = [0] * R
+        return c
 
     def pos_embed(self, h, w):
         if (h, w) not in self._pos_cache:
@@ -73,7 +86,8 @@ class T2IEngine:
 
     @torch.no_grad()
     def gen_tokens(self, cond_emb, uncond_emb, img_start_emb, *, h: int, w: int, num_images: int, guidance_scale: float,
-                   num_sampling_steps: int, num_steps: int | None = None, timers: bool = False):
+                   num_sampling_steps: int, num_steps: int | None = None, timers: bool = False,
+                   use_graph: bool | None = None):
         """cond_emb [Lc, D], uncond_emb [Lu, D] | None, img_start_emb [pn + 2, D] (bf16 embeddings).
         Returns tokens fp32 [B, h*w, zc] (patch-raster order) and packed bits int32 [B, h*w, zc/32]."""
         lib = _lib.load()
@@ -86,7 +100,7 @@ class T2IEngine:
         pos = self.pos_embed(h, w)  # [h*w, D] fp32
         prompts = [cond_emb] + ([uncond_emb] if use_cfg else [])
         max_len = max(p.shape[0] for p in prompts) + 2 + pn + h * w
-        cache = self.llm.new_cache(R, max_len)
+        cache = self._get_cache(R, max_len)
         t0 = time.perf_counter()
         # ---- prefill: causal over [prompt, <vision_start>, <res_h>], then the first block with an all-ones mask ----
         h_fused = torch.empty((R, pn, D), dtype=torch.float32, device=dev)
@@ -106,6 +120,14 @@ class T2IEngine:
         tok_bf = torch.empty((R * pn, self.zc), dtype=torch.bfloat16, device=dev)
         e1 = torch.empty((R * pn, D), dtype=torch.bfloat16, device=dev)
         splits = self.llm.plan_splits(R, pn, max_len)
+        if use_graph is None:
+            use_graph = self.use_graph
+        if use_graph and steps > 2:
+            self._ar_loop_graph(cache, h_fused, pos, tokens, packed, B=B, G=G, hw=h * w, steps=steps,
+                                total_steps=total_steps, guidance_scale=guidance_scale,
+                                num_sampling_steps=num_sampling_steps, splits=splits)
+            steps_done = steps
+            steps = 0
         for step in range(steps):
             x = self.head.sample(h_fused, guidance_scale, num_sampling_steps)  # [B, pn, zc] fp32
             check(lib.bd_sign_tokens_ex(ptr(x), B, pn, self.zc, ptr(tokens), C.c_longlong(h * w),
@@ -122,8 +144,88 @@ class T2IEngine:
         if timers:
             torch.cuda.synchronize()
             self.timings["ar_s"] = time.perf_counter() - t0
-            self.timings["ar_steps"] = steps
+            self.timings["ar_steps"] = steps if steps else steps_done
         return tokens, packed
+
+    # ---- CUDA-graph AR loop ------------------------------------------------------------------------------------------
+    def _ar_step_body(self, st, cache, guidance_scale, num_sampling_steps, splits, with_llm=True):
+        """One AR step on STATIC buffers (graph-capturable): reads st.h_fused / st.pos_cur / st.pos_next, writes
+        st.tok_stage / st.packed_stage and the next st.h_fused."""
+        lib = _lib.load()
+        pn, D = self.pn, self.D
+        x = self.head.sample(st["h_fused"], guidance_scale, num_sampling_steps)
+        check(lib.bd_sign_tokens_ex(ptr(x), st["B"], pn, self.zc, ptr(st["tok_stage"]), C.c_longlong(pn), C.c_longlong(0),
+                                    ptr(st["tok_bf"]), st["G"], ptr(st["packed_stage"]), stream_ptr()),
+              "bd_sign_tokens_ex")
+        if not with_llm:
+            return
+        ops.gemm(st["tok_bf"], self.fc1_w, bias=self.fc1_b, act="gelu_tanh", out=st["e1"], pdl=True)
+        ops.gemm(st["e1"], self.fc2_w, bias=self.fc2_b, res=st["pos_cur"], res_row_mod=pn, out=st["hidden"], pdl=True)
+        R = st["G"] * st["B"]
+        out = self.llm.forward(st["hidden"].view(R, pn, D), cache, 0, R, causal=False, out_add=st["pos_next"],
+                               out_add_mod=pn, attn_splits=splits, sk_bound=cache.max_tokens, track_host=False)
+        st["h_fused"].copy_(out)
+
+    def _ar_loop_graph(self, cache, h_fused, pos, tokens, packed, *, B, G, hw, steps, total_steps, guidance_scale,
+                       num_sampling_steps, splits):
+        """Capture ONE AR step (head sampler + sign + projector + LLM block: ~3 500 kernel launches with their
+        programmatic-dependent-launch edges) into a CUDA graph and replay it per step; per-step inputs (pos-embed blocks)
+        are staged into fixed buffers, per-step outputs (tokens) copied out. Sequence lengths live on the device."""
+        dev, pn, D = self.device, self.pn, self.D
+        R = G * B
+        key = (B, G, guidance_scale, num_sampling_steps, splits, cache.max_tokens)
+        st = self._graph_state.get(key)
+        if st is None:
+            st = dict(B=B, G=G,
+                      h_fused=torch.empty((R, pn, D), dtype=torch.float32, device=dev),
+                      pos_cur=torch.empty((pn, D), dtype=torch.float32, device=dev),
+                      pos_next=torch.empty((pn, D), dtype=torch.float32, device=dev),
+                      tok_stage=torch.empty((B, pn, self.zc), dtype=torch.float32, device=dev),
+                      packed_stage=torch.empty((B, pn, self.zc // 32), dtype=torch.int32, device=dev),
+                      tok_bf=torch.empty((R * pn, self.zc), dtype=torch.bfloat16, device=dev),
+                      e1=torch.empty((R * pn, D), dtype=torch.bfloat16, device=dev),
+                      hidden=torch.empty((R * pn, D), dtype=torch.float32, device=dev), graph=None, cache_id=None)
+            self._graph_state[key] = st
+        st["h_fused"].copy_(h_fused)
+
+        def stage(step):
+            st["pos_cur"].copy_(pos[step * pn:(step + 1) * pn])
+            if step + 1 < total_steps:
+                st["pos_next"].copy_(pos[(step + 1) * pn:(step + 2) * pn])
+
+        def collect(step):
+            tokens[:, step * pn:(step + 1) * pn].copy_(st["tok_stage"])
+            packed[:, step * pn:(step + 1) * pn].copy_(st["packed_stage"])
+
+        first = 0
+        if st["graph"] is None or st["cache_id"] != id(cache.pool):
+            # the graph bakes in the KV pool / page-table / seq_lens addresses of this cache: keep the cache with the graph
+            stage(0)
+            self._ar_step_body(st, cache, guidance_scale, num_sampling_steps, splits)   # eager step 0 = warm-up
+            collect(0)
+            first = 1
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            stage(1)
+            with torch.cuda.graph(g):
+                self._ar_step_body(st, cache, guidance_scale, num_sampling_steps, splits)
+            # capture does not execute: seq_lens was not bumped, h_fused not advanced -> replay step 1 for real
+            st["graph"], st["cache_id"], st["cache"] = g, id(cache.pool), cache
+        else:
+            # re-use the captured graph: it is bound to its own cache object -> copy the prefilled state into it
+            gc = st["cache"]
+            gc.pool.copy_(cache.pool)
+            gc.seq_lens.copy_(cache.seq_lens)
+            gc.host_lens = list(cache.host_lens)
+        for step in range(first, steps):
+            last = step == total_steps - 1
+            stage(step)
+            if last:
+                self._ar_step_body(st, st["cache"], guidance_scale, num_sampling_steps, splits, with_llm=False)
+            else:
+                st["graph"].replay()
+            collect(step)
+
 
     @torch.no_grad()
     def decode(self, tokens, h, w):

@@ -52,3 +52,21 @@ def test_engine_vs_oracle(pn, B, guidance):
     dec_ref = oa.decoder_forward(sds["ae"], grid, rnd=oa.bf16)
     e = (img.float().cpu() - dec_ref).abs().max().item()
     assert e < 4e-2 * dec_ref.abs().max().item() + 2e-2, f"decode err {e}"
+
+
+def test_graph_replay_matches_eager():
+    """The CUDA-graph AR loop must produce exactly the tokens of the eager loop (same kernels, same order)."""
+    eng, sds, LLM = build(16)
+    S, B, h, w, guidance = 3, 1, 16, 16, 3.0
+    emb = sds["llm"]["model.embed_tokens.weight"]
+    bf = lambda ids: emb[ids].to(torch.bfloat16).cuda()
+    args = (bf([5, 17, 33]), bf([3, 4]), bf([400, 401, 401] + [410 + i for i in range(1, 16)]))
+    kw = dict(h=h, w=w, num_images=B, guidance_scale=guidance, num_sampling_steps=S)
+    outs = []
+    for use_graph in (False, True, True):      # second graph run re-uses the captured graph
+        torch.manual_seed(123)
+        t, p = eng.gen_tokens(*args, use_graph=use_graph, **kw)
+        outs.append((t.clone(), p.clone()))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[2][0])
