@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--guidance", type=float, default=7.5)
     ap.add_argument("--ar-steps", type=int, default=None, help="debug only: truncate the AR loop (invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="profiling runs: skip the live dominant-kernel timing")
     ap.add_argument("--graph", type=int, default=1, help="replay the AR step as a CUDA graph (1) or launch it eagerly (0)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -298,7 +299,7 @@ def main():
     ms_ar = 1e3 * phases.get("ar_s", 0.0) / max(ar_steps, 1)
     avg_ctx = 64 / 2 + 2 + pn + (h * w) / 2
     step_bytes = algorithmic_bytes_per_ar_step(R, S, avg_ctx)
-    roof = dominant_kernel_roofline(eng, hbm_peak, peak_src)
+    roof = {} if args.no_roofline else dominant_kernel_roofline(eng, hbm_peak, peak_src)
     roof["ar_step"] = {"algorithmic_gb": step_bytes / 1e9, "ms": ms_ar, "achieved_gbs": step_bytes / 1e9 / (ms_ar / 1e3) if ms_ar else None,
                        "frac": (step_bytes / 1e9 / (ms_ar / 1e3)) / hbm_peak if ms_ar else None}
     line = {

@@ -12,6 +12,7 @@
 #include "bd_host.h"
 #include "bd_ptx.cuh"
 #include "bd_rowops.cuh"
+#include "bd_stream.cuh"
 
 namespace bd {
 
@@ -327,6 +328,234 @@ static HeadWs head_ws_layout(const bd_head_weights_t& w, int M, int n_rows_x, in
   return L;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// persistent path: the whole sampler as one program for bd_stream_kernel (bd_stream.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+struct HeadStreamWs {
+  size_t xb, h, y, mod, a, qkv, o, g, cemb, condb, tfreq, th, temb, part, pred, x, sync, total;
+};
+
+static size_t blocked_bytes(int K) { return static_cast<size_t>((K + 63) / 64) * kSlotBytes; }
+
+static HeadStreamWs head_stream_ws_layout(const bd_head_weights_t& w, int S) {
+  HeadStreamWs L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = (off + bytes + 1023) & ~size_t(1023);
+    return o;
+  };
+  const size_t D = w.D;
+  const size_t n_mod = static_cast<size_t>(w.n_ada) * 6 * D + 2 * D;
+  L.xb = take(blocked_bytes(w.C));
+  L.h = take(128 * D * 2);
+  L.y = take(blocked_bytes(w.D));
+  L.mod = take(128 * n_mod * 2);
+  L.a = take(blocked_bytes(w.D));
+  L.qkv = take(128 * 3 * D * 2);
+  L.o = take(blocked_bytes(w.D));
+  L.g = take(blocked_bytes(w.hidden));
+  L.cemb = take(128 * D * 2);
+  L.condb = take(blocked_bytes(w.Dz));
+  L.tfreq = take(blocked_bytes(256));
+  L.th = take(blocked_bytes(w.D));
+  L.temb = take(128 * D * 2);
+  L.part = take(static_cast<size_t>(4) * 128 * D * 4);
+  L.pred = take(static_cast<size_t>(128) * w.C * 4);
+  L.x = take(static_cast<size_t>(128) * w.C * 4);
+  L.sync = take(64);
+  L.total = off;
+  return L;
+}
+
+static int head_sample_stream(const bd_head_weights_t& w, const float* cond, const float* noise, const float* sched_host,
+                              int B, int pn, int cfg_mult, float cfg, int S, float* x_out, float* trace, void* workspace,
+                              size_t workspace_bytes, cudaStream_t st) {
+  const int R = B * cfg_mult, M = R * pn, nx = B * pn;
+  const int D = w.D, C = w.C, G = w.stream_ctas;
+  BD_REQUIRE(M <= 128 && S + 1 <= kStreamMaxIter && S + 1 <= 128 && G > 0 && G == num_sms());
+  BD_REQUIRE((D % 64) == 0 && (w.Dz % 8) == 0 && C <= 64 && (w.hidden % 8) == 0 && D <= 6144);
+  BD_REQUIRE(4 + 7 * w.n_blocks + 1 + 6 <= kStreamMaxOps);
+  const int n_mod = w.n_ada * 6 * D + 2 * D;
+  const HeadStreamWs L = head_stream_ws_layout(w, S);
+  if (workspace_bytes < L.total) return BD_ERR_WORKSPACE;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  // blocked operands are read in whole 64-column k-blocks and 128-row tiles: padding must be finite (zero)
+  BD_CUDA_TRY(cudaMemsetAsync(base, 0, L.total, st));
+
+  static thread_local StreamProgram prog;
+  prog = StreamProgram{};
+  prog.M = M;
+  prog.n_ctas = G;
+  prog.rows_x = nx;
+  prog.cfg_mult = cfg_mult;
+  prog.cfg = cfg;
+  prog.n_iter = S + 1;
+  prog.sync = reinterpret_cast<unsigned int*>(base + L.sync);
+  for (int i = 0; i <= S; ++i)
+    for (int j = 0; j < 6; ++j) prog.sched[i][j] = sched_host[i * 8 + j];
+  int n = 0;
+  auto gemm_op = [&](const void* W, const void* A, const void* bias, int N, int K, int ksplit, int epi, int act, void* out,
+                     long long ld, bool blocked) {
+    StreamOp& op = prog.ops[n++];
+    op = StreamOp{};
+    op.kind = kOpGemm;
+    op.sub = epi;
+    op.N = N;
+    op.K = K;
+    op.ksplit = ksplit;
+    op.act = act;
+    op.flags = blocked ? 1 : 0;
+    op.wait_prev = 1;
+    op.p0 = W;
+    op.p1 = A;
+    op.p2 = bias;
+    op.o0 = out;
+    op.l0 = ld;
+  };
+  auto row_op_ = [&](int sub) -> StreamOp& {
+    StreamOp& op = prog.ops[n++];
+    op = StreamOp{};
+    op.kind = kOpRow;
+    op.sub = sub;
+    op.wait_prev = 1;
+    op.f0 = 1e-6f;
+    return op;
+  };
+  __nv_bfloat16* mod = reinterpret_cast<__nv_bfloat16*>(base + L.mod);
+  // ---- once per call ----
+  {
+    StreamOp& op = row_op_(kRowCastCond);
+    op.wait_prev = 0;
+    op.p0 = cond;
+    op.o0 = base + L.condb;
+    op.N = w.Dz;
+  }
+  {
+    StreamOp& op = row_op_(kRowTFreq);
+    op.wait_prev = 0;
+    op.o0 = base + L.tfreq;
+    op.N = 256;
+  }
+  {
+    StreamOp& op = row_op_(kRowInit);
+    op.wait_prev = 0;
+    op.p0 = noise;
+    op.o0 = base + L.x;
+    op.o1 = base + L.xb;
+    op.N = C;
+  }
+  gemm_op(w.time0_w, base + L.tfreq, w.time0_b, D, 256, 1, kEpiBias, kActSilu, base + L.th, 0, true);
+  prog.ops[n - 1].i1 = S + 1;  // one row per timestep
+  gemm_op(w.cond_w, base + L.condb, w.cond_b, D, w.Dz, 1, kEpiBias, kActNone, base + L.cemb, D, false);
+  gemm_op(w.time2_w, base + L.th, w.time2_b, D, D, 1, kEpiBias, kActNone, base + L.temb, D, false);
+  prog.ops[n - 1].i1 = S + 1;
+  prog.n_pre = n;
+  // ---- one evaluation + SDE step ----
+  gemm_op(w.input_proj_w, base + L.xb, w.input_proj_b, D, C, 1, kEpiBias, kActNone, base + L.h, D, false);
+  {
+    StreamOp& op = row_op_(kRowSiluAdd);
+    op.p0 = base + L.temb;
+    op.p1 = base + L.cemb;
+    op.o0 = base + L.y;
+    op.N = D;
+  }
+  gemm_op(w.ada_w, base + L.y, w.ada_b, n_mod, D, 1, kEpiBias, kActNone, mod, n_mod, false);
+  {
+    StreamOp& op = row_op_(kRowLnMod);
+    op.p0 = base + L.h;
+    op.p1 = w.blocks[0].norm1_w;
+    op.p2 = w.blocks[0].norm1_b;
+    op.p3 = mod;
+    op.p4 = mod + D;
+    op.l0 = n_mod;
+    op.o0 = base + L.a;
+    op.N = D;
+  }
+  const int switch_freq = w.n_blocks / w.n_ada;
+  const int ks_wo = stream_ksplit_for(D, D, G), ks_w2 = stream_ksplit_for(D, w.hidden, G);
+  const __nv_bfloat16* mf = mod + static_cast<long long>(w.n_ada) * 6 * D;
+  for (int blk = 0; blk < w.n_blocks; ++blk) {
+    const bd_head_block_t& bw = w.blocks[blk];
+    const __nv_bfloat16* md = mod + static_cast<long long>(blk / switch_freq) * 6 * D;
+    gemm_op(bw.wqkv_w, base + L.a, bw.wqkv_b, 3 * D, D, 1, kEpiBias, kActNone, base + L.qkv, 3 * D, false);
+    {
+      StreamOp& op = prog.ops[n++];
+      op = StreamOp{};
+      op.kind = kOpAttn;
+      op.wait_prev = 1;
+      op.p0 = base + L.qkv;
+      op.o0 = base + L.o;
+      op.N = D;
+      op.K = w.head_dim;
+      op.i0 = pn;
+    }
+    gemm_op(bw.wo_w, base + L.o, nullptr, D, D, ks_wo, kEpiPartial, 0, base + L.part, 0, false);
+    {
+      StreamOp& op = row_op_(kRowSplitkLnMod);
+      op.p0 = base + L.part;
+      op.i0 = ks_wo;
+      op.p5 = bw.wo_b;
+      op.p6 = md + 2 * D;
+      op.o1 = base + L.h;
+      op.p1 = bw.norm2_w;
+      op.p2 = bw.norm2_b;
+      op.p3 = md + 3 * D;
+      op.p4 = md + 4 * D;
+      op.l0 = n_mod;
+      op.o0 = base + L.a;
+      op.N = D;
+    }
+    if (w.use_swiglu)
+      gemm_op(bw.w1_w, base + L.a, bw.w1_b, 2 * w.hidden, D, 1, kEpiSwiglu8, 0, base + L.g, 0, true);
+    else
+      gemm_op(bw.w1_w, base + L.a, bw.w1_b, w.hidden, D, 1, kEpiBias, kActSilu, base + L.g, 0, true);
+    gemm_op(bw.w2_w, base + L.g, nullptr, D, w.hidden, ks_w2, kEpiPartial, 0, base + L.part, 0, false);
+    {
+      const bool last = blk + 1 == w.n_blocks;
+      StreamOp& op = row_op_(last ? kRowFinal : kRowSplitkLnMod);
+      op.p0 = base + L.part;
+      op.i0 = ks_w2;
+      op.p5 = bw.w2_b;
+      op.p6 = md + 5 * D;
+      op.o1 = base + L.h;
+      op.l0 = n_mod;
+      op.N = D;
+      if (!last) {
+        const bd_head_block_t& nb = w.blocks[blk + 1];
+        const __nv_bfloat16* mdn = mod + static_cast<long long>((blk + 1) / switch_freq) * 6 * D;
+        op.p1 = nb.norm1_w;
+        op.p2 = nb.norm1_b;
+        op.p3 = mdn;
+        op.p4 = mdn + D;
+        op.o0 = base + L.a;
+      } else {
+        op.p1 = w.final_w;
+        op.p2 = w.final_b;
+        op.p3 = mf;
+        op.p4 = mf + D;
+        op.o0 = base + L.pred;
+        op.o2 = trace;
+        op.i1 = C;
+        op.i2 = w.out_sigmoid;
+      }
+    }
+  }
+  {
+    StreamOp& op = row_op_(kRowSde);
+    op.p0 = base + L.pred;
+    op.p1 = noise;
+    op.o0 = base + L.x;
+    op.o1 = base + L.xb;
+    op.o2 = x_out;
+    op.N = C;
+  }
+  prog.n_body = n - prog.n_pre;
+  prog.n_post = 0;
+  return stream_launch(prog, st);
+}
+
 }  // namespace bd
 
 using namespace bd;
@@ -335,6 +564,7 @@ extern "C" {
 
 size_t bd_head_workspace_bytes(const bd_head_weights_t* w, int B, int pn, int cfg_mult, int S) {
   if (!w || B <= 0 || pn <= 0 || cfg_mult < 1 || cfg_mult > 2 || S < 0) return 0;
+  if (w->w_tiled == 2) return head_stream_ws_layout(*w, S).total;
   return head_ws_layout(*w, B * cfg_mult * pn, B * pn, S).total;
 }
 
@@ -356,6 +586,12 @@ int bd_head_sample(const bd_head_weights_t* wp, const float* cond, const float* 
   BD_REQUIRE(pn <= 64);  // one KV tile per block of parallel tokens
   BD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (w.w_tiled == 2) {
+    if (B * cfg_mult * pn > 128) return BD_ERR_UNSUPPORTED;  // stream-packed weights: one 128-row tile (use the tiled path)
+    BD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+    return head_sample_stream(w, cond, noise, sched_host, B, pn, cfg_mult, cfg, S, x_out, trace, workspace,
+                              workspace_bytes, st);
+  }
   const bool pdl = (flags & 1) != 0;
   const int R = B * cfg_mult, M = R * pn, nx = B * pn;
   const int D = w.D, C = w.C;

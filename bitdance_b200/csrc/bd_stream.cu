@@ -1,0 +1,827 @@
+// bd_stream.cu — the persistent weight-streaming kernel (design notes in bd_stream.cuh), the stream-major weight packer
+// and the C entry points that expose them.
+#include <cfloat>
+#include "bd_stream.cuh"
+
+namespace bd {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GEMM-pass epilogues: NC (32 or 16) consecutive accumulator columns of token row m, packed column n
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m, int n, const float (&acc)[NC],
+                                               int split) {
+  if (m >= M) return;
+  if (op.sub == kEpiPartial) {
+    float* o = reinterpret_cast<float*>(op.o0) + (static_cast<long long>(split) * M + m) * op.N + n;
+#pragma unroll
+    for (int j = 0; j < NC / 4; ++j)
+      reinterpret_cast<float4*>(o)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    return;
+  }
+  float b[NC];
+  if (op.p2) {
+    const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(op.p2) + n;
+#pragma unroll
+    for (int j = 0; j < NC / 8; ++j) {
+      float t[8];
+      bf16x8_to_f(*reinterpret_cast<const uint4*>(bp + 8 * j), t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b[8 * j + i] = t[i];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) b[j] = 0.f;
+  }
+  uint8_t* outb = reinterpret_cast<uint8_t*>(op.o0);
+  if (op.sub == kEpiSwiglu8) {
+    // packed columns: [8 gate | 8 up] per 16-column unit -> 8 outputs per unit at column n/2   (x1, x2 = chunk(w1(a)); silu(x1)*x2)
+#pragma unroll
+    for (int u = 0; u < NC / 16; ++u) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = bf16_round(acc[16 * u + j] + b[16 * u + j]);
+        const float up = bf16_round(acc[16 * u + 8 + j] + b[16 * u + 8 + j]);
+        y[j] = bf16_round(siluf_(g)) * up;
+      }
+      const int oc = (n >> 1) + 8 * u;
+      uint8_t* dst = (op.flags & 1) ? outb + blk_off(m, oc) : outb + (static_cast<long long>(m) * op.l0 + oc) * 2;
+      *reinterpret_cast<uint4*>(dst) = f_to_bf16x8(y);
+    }
+    return;
+  }
+#pragma unroll
+  for (int u = 0; u < NC / 8; ++u) {
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = bf16_round(acc[8 * u + j] + b[8 * u + j]);
+      if (op.act == kActSilu) v = bf16_round(siluf_(v));
+      if (op.act == kActGeluTanh) v = bf16_round(gelu_tanhf_(v));
+      y[j] = v;
+    }
+    const int oc = n + 8 * u;
+    uint8_t* dst = (op.flags & 1) ? outb + blk_off(m, oc) : outb + (static_cast<long long>(m) * op.l0 + oc) * 2;
+    *reinterpret_cast<uint4*>(dst) = f_to_bf16x8(y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row ops: executed by the 128 epilogue threads of CTA r for token row r
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kRowVec = 6;  // D <= 128 * 6 * 8 = 6144
+
+// LN statistics + modulate of a row held in registers; writes `a` blocked (or to smem floats when a_smem != nullptr).
+__device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, float (&v)[kRowVec][8], float sum, float* red,
+                                           const float* ln_w, const float* ln_b, float* a_smem) {
+  const int D = op.N, nvec = D / 8;
+  const float mean = epi_sum(sum, red, tid) / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRowVec; ++i) {
+    const int c = tid + i * 128;
+    if (c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(epi_sum(sq, red, tid) / static_cast<float>(D) + op.f0);
+  const __nv_bfloat16* scale = reinterpret_cast<const __nv_bfloat16*>(op.p3) + static_cast<long long>(r) * op.l0;
+  const __nv_bfloat16* shift = reinterpret_cast<const __nv_bfloat16*>(op.p4) + static_cast<long long>(r) * op.l0;
+  uint8_t* a = reinterpret_cast<uint8_t*>(op.o0);
+#pragma unroll
+  for (int i = 0; i < kRowVec; ++i) {
+    const int c = tid + i * 128;
+    if (c < nvec) {
+      float sc[8], sh[8], o[8];
+      bf16x8_to_f(ldcg_u4(scale + c * 8), sc);
+      bf16x8_to_f(ldcg_u4(shift + c * 8), sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float hn = (v[i][j] - mean) * rstd;
+        if (ln_w) hn = hn * ln_w[c * 8 + j] + ln_b[c * 8 + j];
+        o[j] = hn * bf16_round(1.0f + sc[j]) + sh[j];
+      }
+      if (a_smem) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a_smem[c * 8 + j] = bf16_round(o[j]);
+      } else {
+        *reinterpret_cast<uint4*>(a + blk_off(r, c * 8)) = f_to_bf16x8(o);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp& op, int it, int r, int tid, float* red,
+                                       uint8_t* scratch) {
+  const int M = prog.M;
+  switch (op.sub) {
+    case kRowCastCond: {  // p0 fp32 [M, N] (kernel input) -> o0 blocked bf16
+      if (r >= M) return;
+      const float* src = reinterpret_cast<const float*>(op.p0) + static_cast<long long>(r) * op.N;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(op.o0);
+      for (int c = tid; c < op.N / 8; c += 128) {
+        const float4 x0 = reinterpret_cast<const float4*>(src + c * 8)[0], x1 = reinterpret_cast<const float4*>(src + c * 8)[1];
+        const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        *reinterpret_cast<uint4*>(dst + blk_off(r, c * 8)) = f_to_bf16x8(v);
+      }
+      return;
+    }
+    case kRowTFreq: {  // timestep_embedding (flow_head_parallel_x.py:12-27) of t = sched[r][0], dim N -> o0 blocked bf16
+      if (r >= prog.n_iter) return;
+      const int half = op.N / 2;
+      const float tv = 1000.0f * prog.sched[r][0];
+      uint8_t* dst = reinterpret_cast<uint8_t*>(op.o0);
+      for (int k = tid; k < half; k += 128) {
+        const float f = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+        const float a = tv * f;
+        *reinterpret_cast<__nv_bfloat16*>(dst + blk_off(r, k)) = __float2bfloat16_rn(cosf(a));
+        *reinterpret_cast<__nv_bfloat16*>(dst + blk_off(r, half + k)) = __float2bfloat16_rn(sinf(a));
+      }
+      return;
+    }
+    case kRowInit: {  // x = noise[0]; xb = bf16(x) for every CFG group   (sampling_x.py:60,71)
+      if (r >= prog.rows_x || tid >= op.N) return;
+      const float v = reinterpret_cast<const float*>(op.p0)[static_cast<long long>(r) * op.N + tid];
+      reinterpret_cast<float*>(op.o0)[static_cast<long long>(r) * op.N + tid] = v;
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      uint8_t* xb = reinterpret_cast<uint8_t*>(op.o1);
+      for (int g = 0; g < prog.cfg_mult; ++g) *reinterpret_cast<__nv_bfloat16*>(xb + blk_off(g * prog.rows_x + r, tid)) = b;
+      return;
+    }
+    case kRowSiluAdd: {  // y = bf16(silu(bf16(temb[it] + cemb[r])))   (TransEncoder.forward :330)
+      if (r >= M) return;
+      const __nv_bfloat16* te = reinterpret_cast<const __nv_bfloat16*>(op.p0) + static_cast<long long>(it) * op.N;
+      const __nv_bfloat16* ce = reinterpret_cast<const __nv_bfloat16*>(op.p1) + static_cast<long long>(r) * op.N;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(op.o0);
+      for (int c = tid; c < op.N / 8; c += 128) {
+        float a[8], b[8], o[8];
+        bf16x8_to_f(ldcg_u4(te + c * 8), a);
+        bf16x8_to_f(ldcg_u4(ce + c * 8), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = siluf_(bf16_round(a[j] + b[j]));
+        *reinterpret_cast<uint4*>(dst + blk_off(r, c * 8)) = f_to_bf16x8(o);
+      }
+      return;
+    }
+    case kRowLnMod: {
+      if (r >= M) return;
+      const int nvec = op.N / 8;
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(op.p0) + static_cast<long long>(r) * op.N;
+      float v[kRowVec][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < kRowVec; ++i) {
+        const int c = tid + i * 128;
+        if (c < nvec) {
+          bf16x8_to_f(ldcg_u4(h + c * 8), v[i]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sum += v[i][j];
+        }
+      }
+      row_ln_mod(op, r, tid, v, sum, red, reinterpret_cast<const float*>(op.p1), reinterpret_cast<const float*>(op.p2), nullptr);
+      return;
+    }
+    case kRowSplitkLnMod:
+    case kRowFinal: {
+      // h = bf16(h + bf16(bf16(sum_s partial_s + bias) * gate));  then the LayerNorm-modulate that follows in the network
+      // (TransBlock.forward flow_head_parallel_x.py:242-252; FinalLayer.forward :169-173 for kRowFinal)
+      if (r >= M) return;
+      const int D = op.N, nvec = D / 8, S = op.i0;
+      const float* part = reinterpret_cast<const float*>(op.p0);
+      const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(op.p5);
+      const __nv_bfloat16* gate = reinterpret_cast<const __nv_bfloat16*>(op.p6) + static_cast<long long>(r) * op.l0;
+      __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(op.o1) + static_cast<long long>(r) * D;
+      float v[kRowVec][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < kRowVec; ++i) {
+        const int c = tid + i * 128;
+        if (c < nvec) {
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int s = 0; s < S; ++s) {  // fixed order: deterministic
+            const float* q = part + (static_cast<long long>(s) * M + r) * D + c * 8;
+            const float4 x0 = ldcg_f4(q), x1 = ldcg_f4(q + 4);
+            acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
+            acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+          }
+          float b[8], g[8], res[8];
+          bf16x8_to_f(*reinterpret_cast<const uint4*>(bias + c * 8), b);
+          bf16x8_to_f(ldcg_u4(gate + c * 8), g);
+          bf16x8_to_f(ldcg_u4(h + c * 8), res);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float y = bf16_round(bf16_round(acc[j] + b[j]) * g[j]);
+            v[i][j] = bf16_round(res[j] + y);
+            sum += v[i][j];
+          }
+          *reinterpret_cast<uint4*>(h + c * 8) = f_to_bf16x8(v[i]);
+        }
+      }
+      if (op.sub == kRowSplitkLnMod) {
+        row_ln_mod(op, r, tid, v, sum, red, reinterpret_cast<const float*>(op.p1), reinterpret_cast<const float*>(op.p2), nullptr);
+        return;
+      }
+      // final layer: a (bf16 values) stays in shared memory; o_c = bf16(sum_d a_d Wf[c,d] + bias_c); optional 2*sigmoid-1
+      float* arow = reinterpret_cast<float*>(scratch);
+      row_ln_mod(op, r, tid, v, sum, red, nullptr, nullptr, arow);
+      epi_bar();
+      const int C = op.i1;
+      const __nv_bfloat16* Wf = reinterpret_cast<const __nv_bfloat16*>(op.p1);
+      const __nv_bfloat16* bfin = reinterpret_cast<const __nv_bfloat16*>(op.p2);
+      float* pred = reinterpret_cast<float*>(op.o0);
+      float* trace = reinterpret_cast<float*>(op.o2);
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int c0 = warp * 4; c0 < C; c0 += 16) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int d = lane * 8; d < D; d += 256) {
+          uint4 raw[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            raw[u] = (c0 + u < C) ? *reinterpret_cast<const uint4*>(Wf + static_cast<long long>(c0 + u) * D + d)
+                                  : make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float wv[8];
+            bf16x8_to_f(raw[u], wv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[u] = fmaf(arow[d + j], wv[j], acc[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+        }
+        if (lane < 4 && c0 + lane < C) {
+          float o = bf16_round(acc[lane] + (bfin ? __bfloat162float(bfin[c0 + lane]) : 0.f));
+          if (op.i2) {
+            const float sg = bf16_round(1.0f / (1.0f + expf(-o)));
+            o = bf16_round(bf16_round(2.0f * sg) - 1.0f);
+          }
+          pred[static_cast<long long>(r) * C + c0 + lane] = o;
+          if (trace) trace[(static_cast<long long>(it) * M + r) * C + c0 + lane] = o;
+        }
+      }
+      epi_bar();  // arow (aliasing the A ring) is dead before anything else may touch it
+      return;
+    }
+    case kRowSde: {  // sampling_x.py:24-41 with explicit round-to-nearest ops (torch rounds every op separately)
+      if (r >= prog.rows_x || tid >= op.N) return;
+      const int C = op.N, nx = prog.rows_x;
+      const float* pred = reinterpret_cast<const float*>(op.p0);
+      float* x = reinterpret_cast<float*>(op.o0);
+      const long long i = static_cast<long long>(r) * C + tid;
+      const long long n = static_cast<long long>(nx) * C;
+      const float t = prog.sched[it][0], dt = prog.sched[it][1], denom = prog.sched[it][2], var = prog.sched[it][3],
+                  omt = prog.sched[it][4], nscale = prog.sched[it][5];
+      const bool last = (it == prog.n_iter - 1);
+      const float xv = x[i];
+      float v = __fdiv_rn(__fsub_rn(__ldcg(pred + i), xv), denom);
+      if (prog.cfg_mult == 2) {
+        const float vu = __fdiv_rn(__fsub_rn(__ldcg(pred + n + i), xv), denom);
+        v = __fadd_rn(vu, __fmul_rn(prog.cfg, __fsub_rn(v, vu)));
+      }
+      float xn;
+      if (last) {
+        xn = __fadd_rn(xv, __fmul_rn(v, dt));
+      } else {
+        const float nz = reinterpret_cast<const float*>(op.p1)[static_cast<long long>(it + 1) * n + i];
+        const float score = __fdiv_rn(__fsub_rn(__fmul_rn(t, v), xv), var);
+        const float drift = __fadd_rn(v, __fmul_rn(omt, score));
+        xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(drift, dt)), __fmul_rn(nscale, nz));
+      }
+      x[i] = xn;
+      if (last) {
+        reinterpret_cast<float*>(op.o2)[i] = xn;
+      } else {
+        const __nv_bfloat16 b = __float2bfloat16_rn(xn);
+        uint8_t* xb = reinterpret_cast<uint8_t*>(op.o1);
+        for (int g = 0; g < prog.cfg_mult; ++g) *reinterpret_cast<__nv_bfloat16*>(xb + blk_off(g * nx + r, tid)) = b;
+      }
+      return;
+    }
+    default: return;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// attention over the pn <= 64 tokens of one (sequence, head): Attention.forward flow_head_parallel_x.py:192-220
+// (flash_attn_func semantics: fp32 scores / softmax, P and O in bf16). 128 threads, mma.sync m16n8k16.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void s_ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void s_ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void s_mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t s_pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <int HD>
+__device__ __forceinline__ uint32_t s_tile_off(int row, int chunk) {
+  return static_cast<uint32_t>(row * (HD * 2) + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int HD>
+__device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid, uint8_t* smem) {
+  const int D = op.N, pn = op.i0, H = D / HD;
+  const int seq = unit / H, hd = unit % H;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 64 * HD * 2;
+  uint8_t* sV = sK + 64 * HD * 2;
+  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(op.p0);
+  constexpr int kChunks = HD / 8;
+  for (int i = tid; i < 3 * 64 * kChunks; i += 128) {
+    const int which = i / (64 * kChunks), rem = i % (64 * kChunks);
+    const int rr = rem / kChunks, c = rem % kChunks;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (rr < pn)
+      v = ldcg_u4(qkv + (static_cast<long long>(seq) * pn + rr) * 3 * D + which * D + hd * HD + c * 8);
+    *reinterpret_cast<uint4*>(smem + which * (64 * HD * 2) + s_tile_off<HD>(rr, c)) = v;
+  }
+  epi_bar();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float scale_log2 = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;
+  float s[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ks += 2) {
+    uint32_t a0[4], a1[4];
+    s_ldmatrix_x4(a0, smem_u32(sQ + s_tile_off<HD>(warp * 16 + (lane & 15), 2 * ks + (lane >> 4))));
+    s_ldmatrix_x4(a1, smem_u32(sQ + s_tile_off<HD>(warp * 16 + (lane & 15), 2 * ks + 2 + (lane >> 4))));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t bk[4];
+      s_ldmatrix_x4(bk, smem_u32(sK + s_tile_off<HD>(8 * j + (lane & 7), 2 * ks + (lane >> 3))));
+      s_mma_16816(s[j], a0, bk[0], bk[1]);
+      s_mma_16816(s[j], a1, bk[2], bk[3]);
+    }
+  }
+  float mx[2] = {-FLT_MAX, -FLT_MAX};
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int key = 8 * j + 2 * t + (i & 1);
+      const float v = key < pn ? s[j][i] * scale_log2 : -FLT_MAX;
+      s[j][i] = v;
+      mx[i >> 1] = fmaxf(mx[i >> 1], v);
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+  float l[2] = {0.f, 0.f};
+  uint32_t pa[4][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      e[i] = (s[j][i] == -FLT_MAX) ? 0.f : exp2f(s[j][i] - mx[i >> 1]);
+      l[i >> 1] += e[i];
+    }
+    const int kk = j >> 1;
+    if ((j & 1) == 0) {
+      pa[kk][0] = s_pack_bf16(e[0], e[1]);
+      pa[kk][1] = s_pack_bf16(e[2], e[3]);
+    } else {
+      pa[kk][2] = s_pack_bf16(e[0], e[1]);
+      pa[kk][3] = s_pack_bf16(e[2], e[3]);
+    }
+  }
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int n = 0; n < HD / 8; n += 2) {
+      uint32_t bv[4];
+      s_ldmatrix_x4_trans(bv, smem_u32(sV + s_tile_off<HD>(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), n + (lane >> 4))));
+      s_mma_16816(o_acc[n], pa[kk], bv[0], bv[1]);
+      s_mma_16816(o_acc[n + 1], pa[kk], bv[2], bv[3]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  uint8_t* out = reinterpret_cast<uint8_t*>(op.o0);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qrow = warp * 16 + g + 8 * r;
+    if (qrow >= pn) continue;
+    const float inv = l[r] > 0.f ? 1.0f / l[r] : 0.f;
+    const int row = seq * pn + qrow;
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      const uint32_t pk = s_pack_bf16(o_acc[n][2 * r] * inv, o_acc[n][2 * r + 1] * inv);
+      *reinterpret_cast<uint32_t*>(out + blk_off(row, hd * HD + 8 * n + 2 * t)) = pk;
+    }
+  }
+  epi_bar();  // tiles (aliasing the A ring) dead
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------------
+struct StreamSmem {
+  static constexpr int kW = kStreamWSlots * kSlotBytes;
+  static constexpr int kA = kStreamASlots * kSlotBytes;
+  static constexpr int kBars = (2 * kStreamWSlots + 2 * kStreamASlots + 4) * 8;
+  static constexpr int kTotal = kW + kA + kBars + 64 /*tmem slot + red*/ + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ void op_at(const StreamProgram& prog, int q, int& idx, int& it) {
+  if (q < prog.n_pre) {
+    idx = q;
+    it = 0;
+    return;
+  }
+  const int b = q - prog.n_pre;
+  const int nb = prog.n_body * prog.n_iter;
+  if (b < nb) {
+    it = b / prog.n_body;
+    idx = prog.n_pre + b % prog.n_body;
+    return;
+  }
+  idx = prog.n_pre + prog.n_body + (b - nb);
+  it = prog.n_iter - 1;
+}
+
+__global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __grid_constant__ StreamProgram prog) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + StreamSmem::kW;
+  uint64_t* full_w = reinterpret_cast<uint64_t*>(smem_a + StreamSmem::kA);
+  uint64_t* empty_w = full_w + kStreamWSlots;
+  uint64_t* full_a = empty_w + kStreamWSlots;
+  uint64_t* empty_a = full_a + kStreamASlots;
+  uint64_t* acc_full = empty_a + kStreamASlots;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int c = blockIdx.x;
+  const int G = prog.n_ctas;
+  const int total = prog.n_pre + prog.n_body * prog.n_iter + prog.n_post;
+
+  if (warp == 0 && elect_one()) {
+    for (int s = 0; s < kStreamWSlots; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&empty_w[s], 1);
+    }
+    for (int s = 0; s < kStreamASlots; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== W producer: runs ahead of every dependency =====================
+    if (elect_one()) {
+      uint32_t wi = 0;
+      for (int q = 0; q < total; ++q) {
+        int idx, it;
+        op_at(prog, q, idx, it);
+        const StreamOp& op = prog.ops[idx];
+        if (op.kind != kOpGemm) continue;
+        const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
+        if (part.units == 0) continue;
+        const int rot = stream_k_rot(c, part.kbs);
+        for (int i = 0; i < part.npass; ++i) {
+          const int w = (stream_pass_u0(part, i + 1) - stream_pass_u0(part, i)) * 16;
+          const uint32_t bytes = static_cast<uint32_t>(w) * 128u;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(op.p0) + stream_pass_offset(op.N, part, i) * 2048;
+          for (int t = 0; t < part.kbs; ++t) {
+            int kbl = rot + t;
+            if (kbl >= part.kbs) kbl -= part.kbs;
+            const uint32_t s = wi % kStreamWSlots;
+            if (wi >= kStreamWSlots) mbar_wait(&empty_w[s], ((wi / kStreamWSlots) & 1u) ^ 1u);
+            mbar_expect_tx(&full_w[s], bytes);
+            bulk_g2s(smem_w + s * kSlotBytes, base + static_cast<long long>(kbl) * bytes, bytes, &full_w[s], kEvictFirst);
+            ++wi;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== A producer: waits for the op's grid-wide dependency, then streams the blocked activations
+    if (elect_one()) {
+      uint32_t ai = 0;
+      for (int q = 0; q < total; ++q) {
+        int idx, it;
+        op_at(prog, q, idx, it);
+        const StreamOp& op = prog.ops[idx];
+        if (op.kind != kOpGemm) continue;
+        const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
+        if (part.units == 0) continue;
+        if (op.wait_prev) {
+          grid_wait(prog.sync, static_cast<unsigned int>(G) * static_cast<unsigned int>(q));
+          fence_proxy_async_all();  // other CTAs' generic-proxy stores -> this thread's async-proxy (bulk copy) reads
+        }
+        const int rot = stream_k_rot(c, part.kbs);
+        const uint8_t* abase = reinterpret_cast<const uint8_t*>(op.p1);
+        for (int i = 0; i < part.npass; ++i) {
+          for (int t = 0; t < part.kbs; ++t) {
+            int kbl = rot + t;
+            if (kbl >= part.kbs) kbl -= part.kbs;
+            const uint32_t s = ai % kStreamASlots;
+            if (ai >= kStreamASlots) mbar_wait(&empty_a[s], ((ai / kStreamASlots) & 1u) ^ 1u);
+            mbar_expect_tx(&full_a[s], kSlotBytes);
+            bulk_g2s(smem_a + s * kSlotBytes, abase + static_cast<long long>(part.kb0 + kbl) * kSlotBytes, kSlotBytes,
+                     &full_a[s], kEvictLast);
+            ++ai;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      uint32_t wi = 0, ai = 0, pi = 0;
+      for (int q = 0; q < total; ++q) {
+        int idx, it;
+        op_at(prog, q, idx, it);
+        const StreamOp& op = prog.ops[idx];
+        if (op.kind != kOpGemm) continue;
+        const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
+        if (part.units == 0) continue;
+        for (int i = 0; i < part.npass; ++i) {
+          const int w = (stream_pass_u0(part, i + 1) - stream_pass_u0(part, i)) * 16;
+          const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(w));
+          const uint32_t buf = pi & 1u;
+          if (pi >= 2) mbar_wait(&acc_empty[buf], ((pi >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * 128u;
+          for (int t = 0; t < part.kbs; ++t) {
+            const uint32_t sw = wi % kStreamWSlots, sa = ai % kStreamASlots;
+            mbar_wait(&full_w[sw], (wi / kStreamWSlots) & 1u);
+            mbar_wait(&full_a[sa], (ai / kStreamASlots) & 1u);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + sa * kSlotBytes);
+            const uint32_t w_addr = smem_u32(smem_w + sw * kSlotBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(w_addr + k * 32), idesc,
+                        (t | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_w[sw]);
+            umma_commit(&empty_a[sa]);
+            ++wi;
+            ++ai;
+          }
+          umma_commit(&acc_full[buf]);
+          ++pi;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue / row / attention warps (3..6); TMEM lane quarter = warp % 4 =====================
+    const int tid = threadIdx.x - kStreamEpiWarp0 * 32;
+    const int lane = tid & 31;
+    const int qd = warp & 3;
+    const int m = qd * 32 + lane;
+    uint32_t pi = 0;
+    for (int q = 0; q < total; ++q) {
+      int idx, it;
+      op_at(prog, q, idx, it);
+      const StreamOp& op = prog.ops[idx];
+      if (op.kind == kOpGemm) {
+        const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
+        const int rows = op.i1 > 0 ? op.i1 : prog.M;  // valid token rows of this op
+        for (int i = 0; i < part.npass; ++i) {
+          const int u0 = stream_pass_u0(part, i);
+          const int w = (stream_pass_u0(part, i + 1) - u0) * 16;
+          const int n0 = (part.unit0 + u0) * 16;
+          const uint32_t buf = pi & 1u;
+          mbar_wait(&acc_full[buf], (pi >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t tbase = tmem_base + buf * 128u + (static_cast<uint32_t>(qd * 32) << 16);
+          int col = 0;
+          for (; col + 32 <= w; col += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tbase + static_cast<uint32_t>(col), v);
+            tmem_ld_wait();
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+            gemm_epi_chunk<32>(op, rows, m, n0 + col, acc, part.split);
+          }
+          if (col < w) {
+            uint32_t v[16];
+            tmem_ld_32x32_x16(tbase + static_cast<uint32_t>(col), v);
+            tmem_ld_wait();
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+            gemm_epi_chunk<16>(op, rows, m, n0 + col, acc, part.split);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          ++pi;
+        }
+      } else {
+        if (op.wait_prev) {
+          if (tid == 0) grid_wait(prog.sync, static_cast<unsigned int>(G) * static_cast<unsigned int>(q));
+          epi_bar();
+        }
+        if (op.kind == kOpRow) {
+          row_op(prog, op, it, c, tid, red, smem_a);
+        } else {
+          const int units = (prog.M / op.i0) * (op.N / op.K);
+          if (c < units) {
+            if (op.K == 128) attn_unit<128>(op, c, tid, smem_a);
+            else attn_unit<64>(op, c, tid, smem_a);
+          }
+        }
+        // generic-proxy writes to the A ring (attention tiles / final row) before later async-proxy (bulk copy) writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      // ---- this CTA's part of op q is complete: publish ----
+      epi_bar();
+      if (tid == 0) red_release_gpu_add(prog.sync, 1u);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stream-major weight packing: W [N, K] row-major bf16 -> for CTA c, pass i, k-block kb: a [w x 64] slot in the
+// 128B-swizzled K-major image (contiguous per CTA). perm 1 = SwiGLU-8: packed unit u = [8 rows of x1 | 8 rows of x2].
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __host__ inline int stream_src_row(int p, int perm, int hidden) {
+  if (perm == 0) return p;
+  const int u = p >> 4, wi = p & 15;
+  return wi < 8 ? u * 8 + wi : hidden + u * 8 + (wi - 8);
+}
+
+__global__ void __launch_bounds__(256) stream_pack_kernel(const __nv_bfloat16* __restrict__ w, long long ldw, int N, int K,
+                                                          int S, int G, int perm, int hidden,
+                                                          const __nv_bfloat16* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ out,
+                                                          __nv_bfloat16* __restrict__ bias_out) {
+  const int c = blockIdx.x;
+  const StreamPart part = stream_partition(N, K, S, G, c);
+  if (part.units == 0) return;
+  const int kbl = blockIdx.y;  // local k-block
+  if (kbl >= part.kbs) return;
+  const int kb = part.kb0 + kbl;
+  for (int i = 0; i < part.npass; ++i) {
+    const int u0 = stream_pass_u0(part, i);
+    const int wd = (stream_pass_u0(part, i + 1) - u0) * 16;
+    const int n0 = (part.unit0 + u0) * 16;
+    uint8_t* slot = reinterpret_cast<uint8_t*>(out) + stream_pass_offset(N, part, i) * 2048 +
+                    static_cast<long long>(kbl) * wd * 128;
+    for (int t = threadIdx.x; t < wd * 8; t += blockDim.x) {
+      const int r = t >> 3, j = t & 7;
+      const int src = stream_src_row(n0 + r, perm, hidden);
+      const int k = kb * 64 + j * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (k + 8 <= K && ((ldw & 7) == 0)) {
+        v = *reinterpret_cast<const uint4*>(w + src * ldw + k);
+      } else {
+        __nv_bfloat16 tmp[8];
+        for (int e = 0; e < 8; ++e) tmp[e] = (k + e < K) ? w[src * ldw + k + e] : __float2bfloat16_rn(0.f);
+        v = *reinterpret_cast<uint4*>(tmp);
+      }
+      *reinterpret_cast<uint4*>(slot + r * 128 + ((j ^ (r & 7)) << 4)) = v;
+    }
+    if (bias_out && kbl == 0 && part.split == 0) {
+      for (int r = threadIdx.x; r < wd; r += blockDim.x)
+        bias_out[n0 + r] = bias ? bias[stream_src_row(n0 + r, perm, hidden)] : __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+int stream_launch(const StreamProgram& prog, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BD_CUDA_TRY(cudaFuncSetAttribute(bd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamSmem::kTotal));
+    attr_set = true;
+  }
+  BD_CUDA_TRY(cudaMemsetAsync(prog.sync, 0, sizeof(unsigned int), stream));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(prog.n_ctas);
+  cfg.blockDim = dim3(kStreamThreads);
+  cfg.dynamicSmemBytes = StreamSmem::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ++g_launch_count;
+  BD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bd_stream_kernel, prog));
+  return BD_OK;
+}
+
+}  // namespace bd
+
+using namespace bd;
+
+extern "C" {
+
+int bd_stream_num_ctas(void) { return num_sms(); }
+
+size_t bd_stream_packed_elems(int N, int K) {
+  if (N <= 0 || K <= 0 || (N % 16) != 0) return 0;
+  return static_cast<size_t>(N) * (static_cast<size_t>((K + 63) / 64) * 64);
+}
+
+int bd_stream_ksplit(int N, int K, int n_ctas) { return stream_ksplit_for(N, K, n_ctas); }
+
+int bd_stream_pack_weight(const void* W, int64_t ldw, int N, int K, int ksplit, int n_ctas, int perm, int hidden,
+                          const void* bias, void* out, void* bias_out, bd_stream_t stream) {
+  BD_REQUIRE(W && out && N > 0 && K > 0 && (N % 16) == 0 && ldw >= K && n_ctas > 0 && ksplit >= 1);
+  BD_REQUIRE(((K + 63) / 64) % ksplit == 0 && n_ctas / ksplit >= 1);
+  BD_REQUIRE(perm == 0 || (perm == 1 && hidden > 0 && N == 2 * hidden && (hidden % 8) == 0));
+  const int kbs = ((K + 63) / 64) / ksplit;
+  dim3 grid(n_ctas, kbs);
+  stream_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(W), ldw, N, K, ksplit, n_ctas, perm, hidden,
+      static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(bias_out));
+  BD_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+// n_w GEMM ops x repeat through the persistent kernel (tests / micro-benchmarks): A blocked bf16 [ceil(K/64)][128][64],
+// W stream-packed, out per `epi` (0 bias(+act) -> bf16 row-major or blocked; 1 SwiGLU-8; 2 fp32 partials [ksplit][M][N]).
+int bd_stream_gemm(const void* A_blocked, const void* W_packed, int64_t w_stride_bytes, int n_w, const void* bias_packed,
+                   void* out, int64_t ld_out, int M, int N, int K, int ksplit, int epi, int act, int out_blocked,
+                   int n_ctas, int repeat, void* sync, bd_stream_t stream) {
+  BD_REQUIRE(A_blocked && W_packed && out && sync && M > 0 && M <= 128 && N > 0 && (N % 16) == 0 && K > 0);
+  BD_REQUIRE(n_ctas > 0 && ksplit >= 1 && ((K + 63) / 64) % ksplit == 0 && repeat >= 1 && repeat <= kStreamMaxIter);
+  BD_REQUIRE(n_w >= 1 && n_w <= kStreamMaxOps);
+  static StreamProgram prog;  // large (kernel parameter image); built per call
+  prog = StreamProgram{};
+  prog.n_pre = 0;
+  prog.n_body = n_w;
+  prog.n_iter = repeat;
+  prog.n_post = 0;
+  prog.M = M;
+  prog.n_ctas = n_ctas;
+  prog.rows_x = 0;
+  prog.cfg_mult = 1;
+  prog.sync = static_cast<unsigned int*>(sync);
+  for (int j = 0; j < n_w; ++j) {
+    StreamOp& op = prog.ops[j];
+    op.kind = kOpGemm;
+    op.sub = epi;
+    op.N = N;
+    op.K = K;
+    op.ksplit = ksplit;
+    op.act = act;
+    op.flags = out_blocked ? 1 : 0;
+    op.wait_prev = 1;
+    op.p0 = static_cast<const uint8_t*>(W_packed) + static_cast<long long>(j) * w_stride_bytes;
+    op.p1 = A_blocked;
+    op.p2 = bias_packed;
+    op.o0 = out;
+    op.l0 = ld_out;
+  }
+  return stream_launch(prog, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// bd_stream.cuh — the persistent weight-streaming engine (sm_100a).
+//
+// Measured on B200 (profiles/r01_*): the tcgen05 GEMM reaches ~5.8 TB/s in steady state but a 52-157 MB weight matrix is
+// only 8-24 us of HBM time, and every kernel boundary costs 6-9 us of ramp + drain during which HBM idles. One diffusion
+// head evaluation (reference modeling/vision_head/flow_head_parallel_x.py:325-342) is 27 such GEMMs, 51 evaluations per
+// AR step (sampling_x.py:44-97). So the whole sampler runs as ONE cooperative kernel, one CTA per SM, interpreting a small
+// op program (GEMM / row / attention ops):
+//   * warp 0  — W producer. Weights never depend on activations, so it walks the program AHEAD of everybody else and
+//               keeps the shared-memory ring full across op boundaries: HBM never idles while the other warps wait on a
+//               grid-wide dependency. Weights are pre-packed "stream-major": the bytes CTA c needs for an op are ONE
+//               contiguous range, already in the 128B-swizzled K-major image tcgen05 wants, fetched with 1-D bulk copies
+//               (no tensor map);
+//   * warp 2  — A producer: activations live in HBM/L2 in the same blocked image ([K/64][128 rows][64] bf16, swizzled),
+//               one 16 KB bulk copy per k-block, issued after the grid-wide dependency of the op is satisfied;
+//   * warp 1  — MMA issuer: tcgen05.mma M=128 (token rows) x N=pass width (16..128 weight rows) x K=16, fp32 accumulators
+//               in TMEM, two accumulator buffers so the epilogue of one pass overlaps the MMAs of the next;
+//   * warps 3-6 — epilogue of the GEMM passes (TMEM -> registers -> HBM) and the executors of row ops (LayerNorm-modulate,
+//               split-K reduction + gated residual, SiLU, the final Linear + SDE update) and of the 64x64 attention.
+// Ops are separated by a grid barrier (one monotonic counter; release/acquire at gpu scope). Work split of a GEMM op:
+// N is cut in units of 16 weight rows dealt evenly to the CTAs (and K in `ksplit` ranges when N is small), so all 148
+// SMs stream equal shares of every matrix.
+#pragma once
+#include "bd_host.h"
+#include "bd_ptx.cuh"
+
+namespace bd {
+
+constexpr int kStreamThreads = 224;
+constexpr int kStreamEpiThreads = 128;   // warps 3..6
+constexpr int kStreamEpiWarp0 = 3;
+constexpr int kSlotBytes = 16384;        // 128 rows x 64 bf16
+constexpr int kStreamWSlots = 10;
+constexpr int kStreamASlots = 4;
+constexpr int kStreamMaxOps = 128;
+constexpr int kStreamMaxIter = 104;
+
+enum : int { kOpGemm = 0, kOpRow = 1, kOpAttn = 2 };
+enum : int { kEpiBias = 0, kEpiSwiglu8 = 1, kEpiPartial = 2 };
+enum : int {
+  kRowCastCond = 0,   // fp32 [M, K] -> blocked bf16
+  kRowTFreq = 1,      // timestep embedding rows -> blocked bf16
+  kRowInit = 2,       // x = noise[0]; xb = bf16(x) duplicated per CFG group
+  kRowSiluAdd = 3,    // y = silu(temb[it] + cemb[r]) -> blocked
+  kRowLnMod = 4,      // a = LN(h) (*w + b) * (1 + scale) + shift -> blocked
+  kRowSplitkLnMod = 5,// h += gate * (sum(partials) + bias); then kRowLnMod
+  kRowFinal = 6,      // kRowSplitkLnMod without affine, then final Linear (+ 2 sigmoid - 1) -> pred
+  kRowSde = 7,        // Euler–Maruyama / last Euler step on x; xb for the next evaluation
+};
+
+// One op. Field meaning per kind:
+//  GEMM: p0 = W stream-packed, p1 = A blocked, p2 = bias (packed order), o0 = out, l0 = ld_out (elements), N, K, ksplit,
+//        sub = epilogue kind, act, flags bit0 = out is blocked bf16 (else row-major), i1 = valid rows (0: prog.M)
+//  ROW:  sub = row kind; pointers documented at each row function
+//  ATTN: p0 = qkv row-major bf16 [M, 3D], o0 = out blocked bf16, N = D, K = head_dim
+struct StreamOp {
+  int kind, sub, N, K;
+  int ksplit, act, flags, wait_prev;
+  const void* p0;
+  const void* p1;
+  const void* p2;
+  const void* p3;
+  const void* p4;
+  const void* p5;
+  const void* p6;
+  void* o0;
+  void* o1;
+  void* o2;
+  long long l0, l1;
+  float f0;
+  int i0, i1, i2;
+};
+
+struct StreamProgram {
+  int n_pre, n_body, n_iter, n_post;
+  int M;          // token rows (<= 128)
+  int n_ctas;
+  int rows_x;     // B * pn rows of the sampler state
+  int cfg_mult;
+  float cfg;
+  unsigned int* sync;  // [1] zero before launch
+  float sched[kStreamMaxIter][6];  // per iteration: t, dt, denom, var, 1-t, noise_scale   (sampling_x.py:62-68)
+  StreamOp ops[kStreamMaxOps];
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// work partition of a GEMM op (shared by the packer, the three pipeline roles and the host)
+// ---------------------------------------------------------------------------------------------------------------------
+struct StreamPart {
+  int split;    // k-range index
+  int unit0;    // first 16-row unit of this CTA
+  int units;    // number of 16-row units (0: no work)
+  int kb0;      // first k-block of the split
+  int kbs;      // k-blocks per split
+  int npass;    // passes of <= 8 units (128 weight rows)
+};
+
+__host__ __device__ inline int stream_ksplit_for(int N, int K, int G) {
+  const int U = N / 16, KB = (K + 63) / 64;
+  if (U < 4 * G && (KB % 4) == 0 && KB >= 16) return 4;
+  return 1;
+}
+
+__host__ __device__ inline StreamPart stream_partition(int N, int K, int S, int G, int c) {
+  StreamPart p;
+  const int U = N / 16, KB = (K + 63) / 64;
+  const int Gs = G / S;
+  p.kbs = KB / S;
+  if (c >= Gs * S) {
+    p.split = 0; p.unit0 = 0; p.units = 0; p.kb0 = 0; p.npass = 0;
+    return p;
+  }
+  p.split = c / Gs;
+  const int j = c % Gs;
+  p.unit0 = static_cast<int>((static_cast<long long>(j) * U) / Gs);
+  p.units = static_cast<int>((static_cast<long long>(j + 1) * U) / Gs) - p.unit0;
+  p.kb0 = p.split * p.kbs;
+  p.npass = (p.units + 7) / 8;
+  return p;
+}
+// pass i of a CTA covers units [pass_u0, pass_u1) relative to unit0
+__host__ __device__ inline int stream_pass_u0(const StreamPart& p, int i) { return (i * p.units) / p.npass; }
+// offset (in 2 KB = 16 rows x 64 k x 2 B units) of the first slot of CTA c / pass i
+__host__ __device__ inline long long stream_pass_offset(int N, const StreamPart& p, int i) {
+  const long long U = N / 16;
+  return (static_cast<long long>(p.split) * U + p.unit0 + stream_pass_u0(p, i)) * p.kbs;
+}
+// k rotation: CTAs start their K loop at different k-blocks so that they do not all hit the same L2 lines of A at once
+__host__ __device__ inline int stream_k_rot(int c, int kbs) { return (c * 5) % kbs; }
+
+// byte offset of element (row, col) inside a blocked bf16 activation [K/64][128][64] with the 128-byte swizzle
+__host__ __device__ inline long long blk_off(int row, int col) {
+  return (static_cast<long long>(col >> 6) << 14) + (row << 7) + ((((col >> 3) & 7) ^ (row & 7)) << 4) + ((col & 7) << 1);
+}
+
+struct StreamProgram;
+int stream_launch(const StreamProgram& prog, cudaStream_t stream);  // bd_stream.cu
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Wait until every CTA has completed all ops before sequence number `seq` (counter >= G * seq). Bounded: a protocol bug
+// traps instead of hanging the box.
+__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
+  unsigned int spins = 0;
+  while (ld_acquire_gpu(ctr) < target) {
+    __nanosleep(32);
+    if (++spins > (1u << 24)) {
+      printf("bd_stream: grid barrier timeout block=%d thread=%d target=%u have=%u\n", blockIdx.x, threadIdx.x, target,
+             ld_acquire_gpu(ctr));
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// L2-coherent loads of activations written by other CTAs of this kernel (never through a stale L1 line)
+__device__ __forceinline__ uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float4 ldcg_f4(const void* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void bf16x8_to_f(const uint4& raw, float (&v)[8]) {
+  const __nv_bfloat162* q = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(q[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 f_to_bf16x8(const float (&v)[8]) {
+  uint4 pk;
+  __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  return pk;
+}
+// sum over the 128 epilogue threads (tid = 0..127), red = 8 floats of shared memory
+__device__ __forceinline__ float epi_sum(float v, float* red, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  epi_bar();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  epi_bar();
+  return (red[0] + red[1]) + (red[2] + red[3]);
+}
+#endif  // __CUDACC__
+
+}  // namespace bd

@@ -25,7 +25,7 @@ class HeadBlock(C.Structure):
 class HeadWeights(C.Structure):
     _fields_ = (
         [(n, C.c_int) for n in ("D", "Dz", "C", "hidden", "n_blocks", "n_ada", "head_dim", "use_swiglu", "w_tiled",
-                                "out_sigmoid")]
+                                "out_sigmoid", "stream_ctas", "reserved_")]
         + [(n, C.c_void_p) for n in ("input_proj_w", "input_proj_b", "time0_w", "time0_b", "time2_w", "time2_b",
                                      "cond_w", "cond_b", "ada_w", "ada_b", "final_w", "final_b")]
         + [("blocks", HeadBlock * MAX_BLOCKS)]
@@ -99,7 +99,9 @@ class HeadRunner:
     """Prepacked weights + workspace for one DiffHead on one device."""
 
     def __init__(self, state_dict: dict, *, ch_target, ch_cond, ch_latent, depth_latent, depth_adanln, use_swiglu,
-                 head_dim=128, out_sigmoid=True, time_shift=1.0, device="cuda", prefix="net."):
+                 head_dim=128, out_sigmoid=True, time_shift=1.0, device="cuda", prefix="net.", stream=True, tiled=True):
+        """stream: also pack the weights stream-major for the persistent kernel (used whenever B*cfg_mult*pn <= 128);
+        tiled: keep the tile-major copy for the multi-kernel path (larger batches)."""
         assert depth_latent <= MAX_BLOCKS
         self.device = torch.device(device)
         self.cfg = dict(C=ch_target, Dz=ch_cond, D=ch_latent, n_blocks=depth_latent, n_ada=depth_adanln)
@@ -107,74 +109,102 @@ class HeadRunner:
         self.hidden = int(ch_latent * 1.5)
         self._keep = []  # prepacked tensors (owned here; C side sees raw pointers)
         dev = self.device
+        D, hidden = ch_latent, self.hidden
+        # the persistent kernel needs 16-row units everywhere and one 64-column k-block for the latent bits
+        stream = bool(stream) and D % 64 == 0 and ch_target <= 64 and hidden % 8 == 0 and ch_cond % 8 == 0 and D <= 6144
+        assert stream or tiled
+        self.w = self._build(state_dict, prefix, "tiled", ch_target, ch_cond, depth_latent, depth_adanln, use_swiglu,
+                             head_dim, out_sigmoid) if tiled else None
+        self.w_stream = self._build(state_dict, prefix, "stream", ch_target, ch_cond, depth_latent, depth_adanln,
+                                    use_swiglu, head_dim, out_sigmoid) if stream else None
+        torch.cuda.synchronize(dev)
+        self._ws = {}
+        self._sched = {}
 
-        def bf(name):
-            t = state_dict[prefix + name].detach().to(device=dev, dtype=torch.bfloat16).contiguous()
-            self._keep.append(t)
-            return t
+    def _build(self, state_dict, prefix, kind, ch_target, ch_cond, depth_latent, depth_adanln, use_swiglu, head_dim,
+               out_sigmoid) -> HeadWeights:
+        dev, D, hidden = self.device, self.cfg["D"], self.hidden
+        keep = self._keep
 
-        def f32(name):
-            t = state_dict[prefix + name].detach().to(device=dev, dtype=torch.float32).contiguous()
-            self._keep.append(t)
-            return t
+        def raw(name, dtype=torch.bfloat16):
+            return state_dict[prefix + name].detach().to(device=dev, dtype=dtype).contiguous()
 
-        def pk(t):
-            """tile-major prepack; the row-major copy is dropped"""
-            p = ops.pack_weight(t)
-            self._keep = [k for k in self._keep if k is not t]
-            self._keep.append(p.data)
-            return p.data_ptr()
+        def kept(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        n_ctas = ops.stream_num_ctas() if kind == "stream" else 0
+
+        def lin(wt, bias, *, ksplit=1, swiglu=False):
+            """-> (weight ptr, bias ptr) in the layout of `kind`; the row-major copy is dropped"""
+            if kind == "stream":
+                sw = ops.stream_pack_weight(wt, bias, ksplit=ksplit, swiglu=swiglu, n_ctas=n_ctas)
+                return kept(sw.data), kept(sw.bias)
+            if swiglu:
+                h = wt.shape[0] // 2
+                wt, bias = ops.interleave16(wt[:h], wt[h:], bias[:h], bias[h:])
+            return kept(ops.pack_weight(wt).data), kept(bias)
 
         w = HeadWeights()
-        w.w_tiled = 1
-        w.D, w.Dz, w.C, w.hidden = ch_latent, ch_cond, ch_target, self.hidden
+        w.w_tiled = 2 if kind == "stream" else 1
+        w.stream_ctas = n_ctas
+        w.D, w.Dz, w.C, w.hidden = D, ch_cond, ch_target, hidden
         w.n_blocks, w.n_ada, w.head_dim = depth_latent, depth_adanln, head_dim
         w.use_swiglu, w.out_sigmoid = int(use_swiglu), int(out_sigmoid)
         for field, name in (("input_proj", "input_proj"), ("time0", "time_embed.mlp.0"), ("time2", "time_embed.mlp.2"),
-                            ("cond", "cond_embed"), ("final", "final_layer.linear")):
-            wt = bf(name + ".weight")
-            setattr(w, field + "_w", wt.data_ptr() if field == "final" else pk(wt))
-            setattr(w, field + "_b", bf(name + ".bias").data_ptr())
+                            ("cond", "cond_embed")):
+            wp, bp = lin(raw(name + ".weight"), raw(name + ".bias"))
+            setattr(w, field + "_w", wp)
+            setattr(w, field + "_b", bp)
+        w.final_w, w.final_b = kept(raw("final_layer.linear.weight")), kept(raw("final_layer.linear.bias"))
         ada_names = [f"ada_ln_blocks.{i}" for i in range(depth_adanln)] + ["final_layer.ada_ln_modulation"]
-        tmp = lambda name: state_dict[prefix + name].detach().to(device=dev, dtype=torch.bfloat16)
-        ada_w = torch.cat([tmp(n + ".weight") for n in ada_names], dim=0).contiguous()
-        ada_b = torch.cat([tmp(n + ".bias") for n in ada_names], dim=0).contiguous()
-        self._keep.append(ada_b)
-        w.ada_w, w.ada_b = pk(ada_w), ada_b.data_ptr()
+        ada_w = torch.cat([raw(n + ".weight") for n in ada_names], dim=0).contiguous()
+        ada_b = torch.cat([raw(n + ".bias") for n in ada_names], dim=0).contiguous()
+        w.ada_w, w.ada_b = lin(ada_w, ada_b)
+        del ada_w
+        ks_wo = ops.stream_ksplit(D, D, n_ctas) if kind == "stream" else 1
+        ks_w2 = ops.stream_ksplit(D, hidden, n_ctas) if kind == "stream" else 1
         for i in range(depth_latent):
             b = f"res_blocks.{i}."
             blk = w.blocks[i]
-            blk.norm1_w, blk.norm1_b = f32(b + "norm1.weight").data_ptr(), f32(b + "norm1.bias").data_ptr()
-            blk.norm2_w, blk.norm2_b = f32(b + "norm2.weight").data_ptr(), f32(b + "norm2.bias").data_ptr()
-            blk.wqkv_w, blk.wqkv_b = pk(bf(b + "attn.wqkv.weight")), bf(b + "attn.wqkv.bias").data_ptr()
-            blk.wo_w, blk.wo_b = pk(bf(b + "attn.wo.weight")), bf(b + "attn.wo.bias").data_ptr()
-            if use_swiglu:
-                w1, b1 = bf(b + "w1.weight"), bf(b + "w1.bias")
-                wi, bi = ops.interleave16(w1[: self.hidden], w1[self.hidden:], b1[: self.hidden], b1[self.hidden:])
-                self._keep.append(bi)
-                self._keep = [t for t in self._keep if t is not w1]  # un-interleaved copy not needed
-                blk.w1_w, blk.w1_b = pk(wi), bi.data_ptr()
-                blk.w2_w, blk.w2_b = pk(bf(b + "w2.weight")), bf(b + "w2.bias").data_ptr()
-            else:
-                blk.w1_w, blk.w1_b = pk(bf(b + "mlp.0.weight")), bf(b + "mlp.0.bias").data_ptr()
-                blk.w2_w, blk.w2_b = pk(bf(b + "mlp.2.weight")), bf(b + "mlp.2.bias").data_ptr()
-        torch.cuda.synchronize(dev)
-        self.w = w
-        self._ws = None
-        self._sched = {}
+            blk.norm1_w, blk.norm1_b = kept(raw(b + "norm1.weight", torch.float32)), kept(raw(b + "norm1.bias", torch.float32))
+            blk.norm2_w, blk.norm2_b = kept(raw(b + "norm2.weight", torch.float32)), kept(raw(b + "norm2.bias", torch.float32))
+            blk.wqkv_w, blk.wqkv_b = lin(raw(b + "attn.wqkv.weight"), raw(b + "attn.wqkv.bias"))
+            # wo / w2 go through fp32 partials (split-K) on the persistent path: their bias is applied by the row op
+            wp, _ = lin(raw(b + "attn.wo.weight"), None if kind == "stream" else raw(b + "attn.wo.bias"), ksplit=ks_wo)
+            blk.wo_w, blk.wo_b = wp, kept(raw(b + "attn.wo.bias"))
+            n1, n2 = ("w1", "w2") if use_swiglu else ("mlp.0", "mlp.2")
+            blk.w1_w, blk.w1_b = lin(raw(b + n1 + ".weight"), raw(b + n1 + ".bias"), swiglu=bool(use_swiglu))
+            wp, _ = lin(raw(b + n2 + ".weight"), None if kind == "stream" else raw(b + n2 + ".bias"), ksplit=ks_w2)
+            blk.w2_w, blk.w2_b = wp, kept(raw(b + n2 + ".bias"))
+        return w
 
     def schedule(self, S: int) -> torch.Tensor:
         if S not in self._sched:
             self._sched[S] = sampler_schedule(S, self.time_shift, device=self.device)
         return self._sched[S]
 
-    def _workspace(self, B, pn, mult, S):
+    def _workspace(self, w, B, pn, mult, S):
         lib = _lib.load()
         lib.bd_head_workspace_bytes.restype = C.c_size_t
-        need = lib.bd_head_workspace_bytes(C.byref(self.w), B, pn, mult, S)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws
+        need = lib.bd_head_workspace_bytes(C.byref(w), B, pn, mult, S)
+        key = int(w.w_tiled)
+        if key not in self._ws or self._ws[key].numel() < need:
+            self._ws[key] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws[key]
+
+    def weights_for(self, rows: int, S: int, path: str | None = None) -> HeadWeights:
+        """The persistent single-kernel path when the stream-packed weights exist and the batch is one 128-row tile."""
+        if path == "tiled":
+            assert self.w is not None
+            return self.w
+        ok = self.w_stream is not None and rows <= 128 and S + 1 <= 104
+        if path == "stream":
+            assert ok, "persistent path unavailable for this shape"
+        if ok:
+            return self.w_stream
+        assert self.w is not None, "batch needs the tile-major weights (HeadRunner(tiled=True))"
+        return self.w
 
     def draw_noise(self, B, pn, S):
         """Same generator consumption as sampling_x.py: randn(x_shape) then S x randn_like(x)."""
@@ -185,8 +215,9 @@ class HeadRunner:
         return noise
 
     def sample(self, z: torch.Tensor, cfg: float, num_sampling_steps: int, noise: torch.Tensor | None = None,
-               trace: bool = False, pdl: bool = True):
-        """z: [R, pn, Dz] fp32 (cond rows then uncond rows when cfg > 1). Returns x [B, pn, C] fp32 (+ trace)."""
+               trace: bool = False, pdl: bool = True, path: str | None = None):
+        """z: [R, pn, Dz] fp32 (cond rows then uncond rows when cfg > 1). Returns x [B, pn, C] fp32 (+ trace).
+        path: None = automatic, "stream" = the persistent kernel, "tiled" = the multi-kernel path."""
         lib = _lib.load()
         assert z.is_cuda and z.dim() == 3
         mult = 2 if cfg > 1.0 else 1
@@ -201,9 +232,10 @@ class HeadRunner:
         zc = z.to(torch.float32).contiguous()
         out = torch.empty((B, pn, Cc), dtype=torch.float32, device=self.device)
         tr = torch.empty((S + 1, R * pn, Cc), dtype=torch.float32, device=self.device) if trace else None
-        ws = self._workspace(B, pn, mult, S)
+        w = self.weights_for(R * pn, S, path)
+        ws = self._workspace(w, B, pn, mult, S)
         sched = self.schedule(S)
-        st = lib.bd_head_sample(C.byref(self.w), ptr(zc), ptr(noise), C.c_void_p(sched.data_ptr()), B, pn, mult,
+        st = lib.bd_head_sample(C.byref(w), ptr(zc), ptr(noise), C.c_void_p(sched.data_ptr()), B, pn, mult,
                                 C.c_float(cfg), S, ptr(out), ptr(tr), ptr(ws), C.c_size_t(ws.numel()),
                                 1 if pdl else 0, stream_ptr())
         check(st, "bd_head_sample")

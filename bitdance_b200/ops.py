@@ -222,3 +222,107 @@ def attention(q, k, v, *, causal=False, scale=None, page_table=None, sk=None, sp
         stream_ptr())
     check(st, "bd_attention_bf16")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# persistent weight-streaming engine (csrc/bd_stream.cuh)
+# ---------------------------------------------------------------------------------------------------------------------
+class StreamWeight:
+    """A Linear weight in the stream-major layout of ``bd_stream_pack_weight`` (+ packed bias, logical shape)."""
+
+    __slots__ = ("data", "bias", "N", "K", "ksplit", "n_ctas", "perm")
+
+    def __init__(self, data, bias, N, K, ksplit, n_ctas, perm):
+        self.data, self.bias, self.N, self.K, self.ksplit, self.n_ctas, self.perm = data, bias, N, K, ksplit, n_ctas, perm
+
+    def data_ptr(self):
+        return self.data.data_ptr()
+
+
+def stream_num_ctas() -> int:
+    return int(_lib.load().bd_stream_num_ctas())
+
+
+def stream_ksplit(N: int, K: int, n_ctas: int | None = None) -> int:
+    return int(_lib.load().bd_stream_ksplit(N, K, n_ctas or stream_num_ctas()))
+
+
+def stream_pack_weight(w: torch.Tensor, bias: torch.Tensor | None = None, *, ksplit: int = 1, swiglu: bool = False,
+                       n_ctas: int | None = None) -> StreamWeight:
+    """[N, K] bf16 row-major -> stream-major (one-time prepack). swiglu: rows [0, N/2) = x1, [N/2, N) = x2 of a SwiGLU
+    Linear, packed as 8+8 row units so that one accumulator chunk holds matching gate/up columns."""
+    lib = _lib.load()
+    require_cuda(w, bias)
+    assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
+    N, K = w.shape
+    n_ctas = n_ctas or stream_num_ctas()
+    lib.bd_stream_packed_elems.restype = C.c_size_t
+    n = lib.bd_stream_packed_elems(N, K)
+    assert n > 0, "N must be a multiple of 16"
+    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    bout = torch.empty(N, dtype=torch.bfloat16, device=w.device)
+    if bias is not None:
+        bias = bias.to(torch.bfloat16).contiguous()
+    check(lib.bd_stream_pack_weight(ptr(w), C.c_int64(w.stride(0)), N, K, ksplit, n_ctas, 1 if swiglu else 0,
+                                    N // 2 if swiglu else 0, ptr(bias), ptr(out), ptr(bout), stream_ptr()),
+          "bd_stream_pack_weight")
+    return StreamWeight(out, bout, N, K, ksplit, n_ctas, 1 if swiglu else 0)
+
+
+def _blocked_index(rows: int, K: int, device):
+    """element offsets (in bf16 elements) of (row, col) inside a blocked activation [ceil(K/64)][128][64], 128B swizzle"""
+    r = torch.arange(rows, device=device).view(-1, 1)
+    c = torch.arange(K, device=device).view(1, -1)
+    return (c // 64) * 8192 + r * 64 + ((((c // 8) % 8) ^ (r % 8)) * 8) + (c % 8)
+
+
+def to_blocked(a: torch.Tensor) -> torch.Tensor:
+    """[M <= 128, K] bf16 -> the blocked, swizzled image the stream engine reads as a GEMM operand (zero padded)."""
+    M, K = a.shape
+    assert M <= 128 and a.dtype == torch.bfloat16
+    out = torch.zeros(((K + 63) // 64) * 8192, dtype=torch.bfloat16, device=a.device)
+    out[_blocked_index(M, K, a.device).reshape(-1)] = a.reshape(-1)
+    return out
+
+
+def from_blocked(b: torch.Tensor, M: int, K: int) -> torch.Tensor:
+    return b[_blocked_index(M, K, b.device).reshape(-1)].view(M, K)
+
+
+def stream_gemm(a: torch.Tensor, ws: "StreamWeight | list[StreamWeight]", *, epi: str = "bias", act: str | None = None,
+                out_blocked: bool = False, repeat: int = 1, a_is_blocked: bool = False, M: int | None = None):
+    """One (or several identical-shape) GEMM op(s) through the persistent kernel. epi: 'bias' | 'swiglu' | 'partial'.
+    Returns the output of the LAST weight: [M, N] bf16 ('bias'), [M, N/2] bf16 ('swiglu') or fp32 [ksplit, M, N]."""
+    lib = _lib.load()
+    wl = ws if isinstance(ws, (list, tuple)) else [ws]
+    w0 = wl[0]
+    if len(wl) > 1:
+        stride = wl[1].data_ptr() - wl[0].data_ptr()
+        assert all(wl[i].data_ptr() - wl[0].data_ptr() == i * stride for i in range(len(wl)))
+    else:
+        stride = 0
+    if not a_is_blocked:
+        M = a.shape[0]
+        ab = to_blocked(a)
+    else:
+        ab = a
+    N, K, dev = w0.N, w0.K, w0.data.device
+    kind = {"bias": 0, "swiglu": 1, "partial": 2}[epi]
+    if kind == 2:
+        out = torch.zeros((w0.ksplit, M, N), dtype=torch.float32, device=dev)
+        ld = 0
+    else:
+        n_out = N // 2 if kind == 1 else N
+        if out_blocked:
+            out = torch.zeros(((n_out + 63) // 64) * 8192, dtype=torch.bfloat16, device=dev)
+            ld = 0
+        else:
+            out = torch.zeros((M, n_out), dtype=torch.bfloat16, device=dev)
+            ld = n_out
+    sync = torch.zeros(16, dtype=torch.int32, device=dev)
+    check(lib.bd_stream_gemm(ptr(ab), ptr(w0.data), C.c_int64(stride), len(wl), ptr(w0.bias) if kind != 2 else None,
+                             ptr(out), C.c_int64(ld), M, N, K, w0.ksplit, kind, ACT[act], 1 if out_blocked else 0,
+                             w0.n_ctas, repeat, ptr(sync), stream_ptr()), "bd_stream_gemm")
+    if kind != 2 and out_blocked:
+        return from_blocked(out, M, n_out)
+    return out

@@ -148,8 +148,13 @@ typedef struct {
   int n_ada;    /* depth_adanln */
   int head_dim; /* 128 (modeling/) or 64 (imagenet_gen/) */
   int use_swiglu;
-  int w_tiled;     /* 1: every Linear weight below (except final_w) is in bd_pack_weight_tiles layout */
+  int w_tiled;     /* 1: every Linear weight below (except final_w) is in bd_pack_weight_tiles layout;
+                    * 2: stream-major (bd_stream_pack_weight, n_ctas = stream_ctas; w1 with perm 1 + its packed bias when
+                    *    use_swiglu; wo / w2 packed with ksplit = bd_stream_ksplit(D, K, stream_ctas), all others ksplit 1):
+                    *    bd_head_sample then runs the whole sampler as ONE persistent kernel when B*cfg_mult*pn <= 128 */
   int out_sigmoid; /* 1: 2*sigmoid(.)-1 (flow_head_parallel_x.py:341-342); 0: imagenet_gen diff_head_parallel.py:310 */
+  int stream_ctas; /* w_tiled == 2: the CTA count the weights were packed for (bd_stream_num_ctas()) */
+  int reserved_;
   const void *input_proj_w, *input_proj_b;
   const void *time0_w, *time0_b, *time2_w, *time2_b; /* time_embed.mlp.0 / .2 */
   const void *cond_w, *cond_b;
@@ -254,6 +259,34 @@ size_t bd_groupnorm_workspace_bytes(int B, long long HW);
  * beta = Linear(mean(z)) over the +-1 grid z (bf16 NHWC [B, hw, Cz]); outputs fp32 [B, C] holding bf16 values. */
 int bd_adagn_params(const void* z, int B, int hw, int Cz, const void* gamma_w, const void* gamma_b, const void* beta_w,
                     const void* beta_b, int C, float* gamma, float* beta, bd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Persistent weight-streaming engine (csrc/bd_stream.cuh): one cooperative kernel, one CTA per SM, interprets a program
+ * of GEMM / row / attention ops with the weight stream running ahead of every dependency. No reference counterpart (the
+ * reference launches ~100 eager kernels per head evaluation, flow_head_parallel_x.py:325-342); used by bd_head_sample.
+ * ---------------------------------------------------------------------------------------------- */
+int bd_stream_num_ctas(void); /* CTAs of the persistent kernel = SMs of the current device */
+/* k-split the engine uses for a Linear whose output goes through fp32 partials (N small next to the SM count) */
+int bd_stream_ksplit(int N, int K, int n_ctas);
+size_t bd_stream_packed_elems(int N, int K); /* bf16 elements of a stream-packed [N, K] weight (K padded to 64) */
+/* W [N, K] row-major bf16 (ldw) -> stream-major: the weight bytes CTA c needs are one contiguous range, already in the
+ * 128B-swizzled K-major shared-memory image. perm 0: rows as they are; perm 1 (SwiGLU, N = 2*hidden): packed unit u =
+ * [rows 8u..8u+7 of W[:hidden] | rows 8u..8u+7 of W[hidden:]]. bias (nullable) -> bias_out [N] in packed row order. */
+int bd_stream_pack_weight(const void* W, int64_t ldw, int N, int K, int ksplit, int n_ctas, int perm, int hidden,
+                          const void* bias, void* out, void* bias_out, bd_stream_t stream);
+/* n_w GEMMs (weights W_packed + j * w_stride_bytes) x `repeat` through the persistent kernel — tests / micro-benchmarks.
+ * A: blocked bf16 [ceil(K/64)][128][64] (128B-swizzled rows; see tests/test_stream_gpu.py); epi 0: bf16(act(acc + bias)),
+ * row-major (ld_out) or blocked; epi 1: SwiGLU-8 -> [M, N/2]; epi 2: fp32 partials [ksplit][M][N]. sync: 4 bytes. */
+int bd_stream_gemm(const void* A_blocked, const void* W_packed, int64_t w_stride_bytes, int n_w, const void* bias_packed,
+                   void* out, int64_t ld_out, int M, int N, int K, int ksplit, int epi, int act, int out_blocked,
+                   int n_ctas, int repeat, void* sync, bd_stream_t stream);
+
+/* ---- measurement only (scripts/stream_probe.py; not on the product path, replaces nothing in the reference) ----
+ * Streams n_ctas * w_per_cta bytes of `w` HBM -> shared memory through the same bulk-copy/mbarrier ring the GEMM uses
+ * (w_stages x w_chunk bytes per CTA) and, when x_chunk > 0, re-reads x_chunk bytes of the L2-resident buffer `x` per W
+ * chunk in every CTA (the activation re-read of a weight-streaming GEMM). Gives the ceiling the GEMM is judged against. */
+int bd_probe_stream(const void* w, long long w_per_cta, int w_chunk, int w_stages, const void* x, int x_bytes,
+                    int x_chunk, int x_stages, int n_ctas, bd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -25,14 +25,16 @@ def make(cfg, seed=1, std=0.05):
     (dict(ch_target=16, ch_cond=256, ch_latent=256, depth_latent=2, depth_adanln=2, head_dim=64, out_sigmoid=False),
      2, 4, 2.0, 5),
 ])
-def test_head_sample_vs_oracle(cfg, B, pn, guidance, S):
+@pytest.mark.parametrize("path", ["stream", "tiled"])
+def test_head_sample_vs_oracle(cfg, B, pn, guidance, S, path):
+    """path "stream": the whole sampler as ONE persistent kernel (bd_stream.cuh); "tiled": the multi-kernel path."""
     from oracle import head as oh
     sd, runner = make(cfg)
     torch.manual_seed(0)
     mult = 2 if guidance > 1.0 else 1
     z = torch.randn(B * mult, pn, cfg["ch_cond"])
     noise = torch.randn(S + 1, B, pn, cfg["ch_target"])
-    x, trace = runner.sample(z.cuda(), guidance, S, noise=noise.cuda(), trace=True)
+    x, trace = runner.sample(z.cuda(), guidance, S, noise=noise.cuda(), trace=True, path=path)
     torch.cuda.synchronize()
     hd, osig = cfg.get("head_dim", 128), cfg.get("out_sigmoid", True)
     # (1) teacher-forced parity: drive the oracle sampler with the GPU's own network outputs. Then
@@ -50,7 +52,7 @@ def test_head_sample_vs_oracle(cfg, B, pn, guidance, S):
     ref = oh.euler_maruyama(sd, z, guidance, S, list(noise), rnd=oh.bf16, head_dim=hd, out_sigmoid=osig)[:B]
     d = (x.cpu() - ref).abs()
     agree = (torch.sign(x.cpu()) == torch.sign(ref)).float().mean().item()
-    print(f"head parity: teacher-forced net max err {e_net:.4f} (scale {scale:.2f}), sampler err {e_sde:.2e}; "
+    print(f"head parity [{path}]: teacher-forced net max err {e_net:.4f} (scale {scale:.2f}), sampler err {e_sde:.2e}; "
           f"free-running max {d.max().item():.4f} mean {d.mean().item():.5f} sign agreement {agree:.4f}")
     assert e_net < 4.7e-2 * scale, f"network output err {e_net}"   # 6 bf16 ulps at |out| ~ 1 (2^-8 spacing)
     assert e_sde < 1e-4 * max(1.0, x_tf.abs().max().item()), f"sampler arithmetic err {e_sde}"
@@ -61,11 +63,12 @@ def test_head_sampler_deterministic_and_seeded_noise():
     cfg = dict(ch_target=32, ch_cond=256, ch_latent=256, depth_latent=2, depth_adanln=2)
     sd, runner = make(cfg)
     z = torch.randn(2, 16, 256, device="cuda")
-    torch.manual_seed(7)
-    a = runner.sample(z, 2.0, 3)
-    torch.manual_seed(7)
-    b = runner.sample(z, 2.0, 3)
-    assert torch.equal(a, b)
+    for path in ("stream", "tiled"):
+        torch.manual_seed(7)
+        a = runner.sample(z, 2.0, 3, path=path)
+        torch.manual_seed(7)
+        b = runner.sample(z, 2.0, 3, path=path)
+        assert torch.equal(a, b), path
     # the noise consumption matches the reference sampler's call sequence: randn(x0) then randn_like per step
     torch.manual_seed(7)
     n0 = torch.randn(1, 16, 32, device="cuda")

@@ -1,0 +1,105 @@
+"""The persistent weight-streaming engine (csrc/bd_stream.cuh): layout helpers on CPU, GEMM ops vs torch on the GPU.
+
+Tolerances: bf16 output rounding + fp32 accumulation order (the engine rotates the K loop per CTA), as for bd_gemm_bf16."""
+import pytest
+import torch
+
+
+def test_blocked_layout_roundtrip_cpu():
+    """to_blocked / from_blocked are inverse and follow the 128B-swizzle rule chunk' = chunk ^ (row % 8)."""
+    from bitdance_b200 import ops
+    a = torch.arange(100 * 200, dtype=torch.float32).view(100, 200).to(torch.bfloat16)
+    b = ops.to_blocked(a)
+    assert b.numel() == 4 * 8192
+    assert torch.equal(ops.from_blocked(b, 100, 200), a)
+    # element (row 3, col 8*5+2) of k-block 1 sits in 16-byte chunk 5^3 = 6 of its 128-byte row
+    r, c = 3, 64 + 8 * 5 + 2
+    assert b[8192 + r * 64 + (5 ^ 3) * 8 + 2] == a[r, c]
+    # padding is zero
+    assert float(b.float().abs().sum()) == float(a.float().abs().sum())
+
+
+def _ref_linear(a, w, bias):
+    return a.float() @ w.float().t() + (bias.float() if bias is not None else 0.0)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,act,blocked", [
+    (128, 2048 + 16, 512, None, False),
+    (128, 7680, 1024, "silu", True),
+    (64, 1024, 256 + 32, None, False),     # ragged K (zero padded k-block), M < 128
+    (16, 160, 64, "gelu_tanh", False),     # fewer 16-row units than CTAs
+])
+def test_stream_gemm_bias(M, N, K, act, blocked):
+    from bitdance_b200 import ops
+    torch.manual_seed(0)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    b = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16)
+    sw = ops.stream_pack_weight(w, b)
+    out = ops.stream_gemm(a, sw, epi="bias", act=act, out_blocked=blocked).float()
+    ref = _bf(_ref_linear(a, w, b))
+    if act == "silu":
+        ref = _bf(torch.nn.functional.silu(ref))
+    if act == "gelu_tanh":
+        ref = _bf(torch.nn.functional.gelu(ref, approximate="tanh"))
+    err = (out - ref).abs().max().item()
+    assert err <= 1.5e-2 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,hidden,K", [(128, 1536, 512), (48, 384, 256)])
+def test_stream_gemm_swiglu(M, hidden, K):
+    from bitdance_b200 import ops
+    torch.manual_seed(1)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(2 * hidden, K, device="cuda") * 0.05).to(torch.bfloat16)
+    b = (torch.randn(2 * hidden, device="cuda") * 0.1).to(torch.bfloat16)
+    sw = ops.stream_pack_weight(w, b, swiglu=True)
+    out = ops.stream_gemm(a, sw, epi="swiglu", out_blocked=True).float()
+    y = _bf(_ref_linear(a, w, b))
+    ref = _bf(_bf(torch.nn.functional.silu(y[:, :hidden])) * y[:, hidden:])
+    err = (out - ref).abs().max().item()
+    assert out.shape == (M, hidden)
+    assert err <= 1.5e-2 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,ksplit", [(128, 1024, 1024, 4), (128, 5120, 2048, 4), (32, 256, 1024, 1)])
+def test_stream_gemm_partials(M, N, K, ksplit):
+    from bitdance_b200 import ops
+    torch.manual_seed(2)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    sw = ops.stream_pack_weight(w, None, ksplit=ksplit)
+    part = ops.stream_gemm(a, sw, epi="partial")
+    assert part.shape == (ksplit, M, N)
+    ref = _ref_linear(a, w, None)
+    err = (part.sum(0) - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-4, err
+    # each split holds exactly its K range
+    ks = K // ksplit
+    for s in range(ksplit):
+        rs = a[:, s * ks:(s + 1) * ks].float() @ w[:, s * ks:(s + 1) * ks].float().t()
+        assert (part[s] - rs).abs().max().item() <= 2e-3 * rs.abs().max().item() + 1e-4
+
+
+@pytest.mark.gpu
+def test_stream_gemm_chain_of_weights_and_repeat():
+    """several ops and iterations in one launch: the W producer runs across op boundaries; results stay those of the last op"""
+    from bitdance_b200 import ops
+    torch.manual_seed(3)
+    M, N, K = 128, 3072, 768
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    ws = [(torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16) for _ in range(3)]
+    packed = [ops.stream_pack_weight(w, None) for w in ws]
+    big = torch.cat([p.data for p in packed])
+    n = packed[0].data.numel()
+    views = [ops.StreamWeight(big[i * n:(i + 1) * n], packed[0].bias, N, K, 1, packed[0].n_ctas, 0) for i in range(3)]
+    out = ops.stream_gemm(a, views, epi="bias", repeat=5).float()
+    ref = _bf(_ref_linear(a, ws[-1], None))
+    assert (out - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item() + 1e-3
