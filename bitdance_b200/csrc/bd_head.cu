@@ -568,6 +568,25 @@ size_t bd_head_workspace_bytes(const bd_head_weights_t* w, int B, int pn, int cf
   return head_ws_layout(*w, B * cfg_mult * pn, B * pn, S).total;
 }
 
+// debug / tests: byte offsets of the workspace regions (order of the HeadWs / HeadStreamWs fields), returns the count
+int bd_head_ws_offsets(const bd_head_weights_t* w, int B, int pn, int cfg_mult, int S, size_t* out, int cap) {
+  if (!w || !out) return 0;
+  if (w->w_tiled == 2) {
+    const HeadStreamWs L = head_stream_ws_layout(*w, S);
+    const size_t v[] = {L.xb, L.h, L.y, L.mod, L.a, L.qkv, L.o, L.g, L.cemb, L.condb, L.tfreq, L.th, L.temb, L.part, L.pred,
+                        L.x, L.sync, L.total};
+    const int n = static_cast<int>(sizeof(v) / sizeof(v[0]));
+    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+  }
+  const HeadWs L = head_ws_layout(*w, B * cfg_mult * pn, B * pn, S);
+  const size_t v[] = {L.xb, L.h, L.a, L.o, L.qkv, L.g, L.y, L.mod, L.cemb, L.tfreq, L.th, L.temb, L.pred, L.x, L.condb,
+                      L.tvals, L.gemm, L.total};
+  const int n = static_cast<int>(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+  return n;
+}
+
 #define BD_TRY(expr)          \
   do {                        \
     int _rc = (expr);         \

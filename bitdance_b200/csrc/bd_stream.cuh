@@ -29,8 +29,11 @@ constexpr int kStreamThreads = 224;
 constexpr int kStreamEpiThreads = 128;   // warps 3..6
 constexpr int kStreamEpiWarp0 = 3;
 constexpr int kSlotBytes = 16384;        // 128 rows x 64 bf16
-constexpr int kStreamWSlots = 10;
-constexpr int kStreamASlots = 4;
+constexpr int kKbPerStep = 2;            // k-blocks per ring slot: one mbarrier round trip / MMA batch per 128 k
+constexpr int kStepBytes = kKbPerStep * kSlotBytes;
+constexpr int kStreamSlots = 7;          // shared-memory ring slots (32 KB each) in total (W ring + A ring)
+constexpr int kStreamWSlotsDefault = 5;
+constexpr int kStreamASlotsDefault = 2;
 constexpr int kStreamMaxOps = 128;
 constexpr int kStreamMaxIter = 104;
 
@@ -78,6 +81,10 @@ struct StreamProgram {
   int cfg_mult;
   float cfg;
   unsigned int* sync;  // [1] zero before launch
+  unsigned long long* dbg;  // optional timeline [dbg_ops][n_ctas][8] of %globaltimer stamps (bd_stream_set_debug)
+  int dbg_ops;
+  int dbg_mode;   // experiment switches (bd_stream_set_debug): bit0 no bias loads, bit1 no stores, bit2 32-byte stores
+  int w_slots, a_slots;  // ring split, w_slots + a_slots <= kStreamSlots (0: defaults)
   float sched[kStreamMaxIter][6];  // per iteration: t, dt, denom, var, 1-t, noise_scale   (sampling_x.py:62-68)
   StreamOp ops[kStreamMaxOps];
 };
@@ -124,8 +131,10 @@ __host__ __device__ inline long long stream_pass_offset(int N, const StreamPart&
   const long long U = N / 16;
   return (static_cast<long long>(p.split) * U + p.unit0 + stream_pass_u0(p, i)) * p.kbs;
 }
-// k rotation: CTAs start their K loop at different k-blocks so that they do not all hit the same L2 lines of A at once
-__host__ __device__ inline int stream_k_rot(int c, int kbs) { return (c * 5) % kbs; }
+// the K loop advances in steps of kKbPerStep k-blocks (the last step may be short); rotation: CTAs start at different
+// steps so that they do not all hit the same L2 lines of A at once
+__host__ __device__ inline int stream_steps(int kbs) { return (kbs + kKbPerStep - 1) / kKbPerStep; }
+__host__ __device__ inline int stream_k_rot(int c, int nsteps) { return (c * 3) % nsteps; }
 
 // byte offset of element (row, col) inside a blocked bf16 activation [K/64][128][64] with the 128-byte swizzle
 __host__ __device__ inline long long blk_off(int row, int col) {
@@ -145,6 +154,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
       :
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(hint)
       : "memory");
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {

@@ -176,6 +176,9 @@ int bd_head_sample(const bd_head_weights_t* w, const float* cond, const float* n
                    int pn, int cfg_mult, float cfg, int S, float* x_out, float* trace, void* workspace,
                    size_t workspace_bytes, int flags, bd_stream_t stream);
 size_t bd_head_workspace_bytes(const bd_head_weights_t* w, int B, int pn, int cfg_mult, int S);
+/* tests / debugging: byte offsets of the named regions inside the workspace (xb, h, ... in the order documented in
+ * csrc/bd_head.cu for the weights' layout kind); returns how many were written (<= cap). */
+int bd_head_ws_offsets(const bd_head_weights_t* w, int B, int pn, int cfg_mult, int S, size_t* out, int cap);
 
 /* ------------------------------------------------------------------------------------------------
  * Qwen3 decoder stack with a paged KV cache
@@ -266,6 +269,14 @@ int bd_adagn_params(const void* z, int B, int hw, int Cz, const void* gamma_w, c
  * reference launches ~100 eager kernels per head evaluation, flow_head_parallel_x.py:325-342); used by bd_head_sample.
  * ---------------------------------------------------------------------------------------------- */
 int bd_stream_num_ctas(void); /* CTAs of the persistent kernel = SMs of the current device */
+/* profiling aid: when buf != NULL every later persistent launch records, for its first max_ops ops, 8 %globaltimer stamps
+ * per (op, CTA) into buf (uint64 [max_ops][n_ctas][8]): 0 A loads start, 1 first MMA, 2 last MMA issued, 3 accumulator
+ * ready, 4 epilogue/row work done, 5 arrival published. NULL switches it off. */
+int bd_stream_set_debug(void* buf, int max_ops);
+/* tuning / experiments: split of the 7 shared-memory ring slots (32 KB = two 64-wide k-blocks each) between weights and
+ * activations (default 5 + 2; the activation ring needs >= 2 slots, it also hosts the attention tiles), and epilogue
+ * experiment switches (0 = product behaviour; bit0 no bias loads, bit1 no stores — measurement only, results are wrong) */
+int bd_stream_set_tuning(int w_slots, int a_slots, int mode);
 /* k-split the engine uses for a Linear whose output goes through fp32 partials (N small next to the SM count) */
 int bd_stream_ksplit(int N, int K, int n_ctas);
 size_t bd_stream_packed_elems(int N, int K); /* bf16 elements of a stream-packed [N, K] weight (K padded to 64) */
