@@ -299,7 +299,7 @@ def main():
     ms_ar = 1e3 * phases.get("ar_s", 0.0) / max(ar_steps, 1)
     avg_ctx = 64 / 2 + 2 + pn + (h * w) / 2
     step_bytes = algorithmic_bytes_per_ar_step(R, S, avg_ctx)
-    roof = {} if args.no_roofline else dominant_kernel_roofline(eng, hbm_peak, peak_src)
+    roof = {} if args.no_roofline else dominant_kernel_roofline(eng, hbm_peak, peak_src, S, args.guidance, B)
     roof["ar_step"] = {"algorithmic_gb": step_bytes / 1e9, "ms": ms_ar, "achieved_gbs": step_bytes / 1e9 / (ms_ar / 1e3) if ms_ar else None,
                        "frac": (step_bytes / 1e9 / (ms_ar / 1e3)) / hbm_peak if ms_ar else None}
     line = {
@@ -326,44 +326,67 @@ def main():
         dist.destroy_process_group()
 
 
-def dominant_kernel_roofline(eng, hbm_peak, peak_src):
-    """bd_gemm_kernel<128> at the head's wqkv shape (M=128, N=15360, K=5120: 157 MB of bf16 weights per launch — the
-    shape that dominates the step's bytes), weights in the tile-major layout the engine uses. Timed live with CUDA
-    events on the launching stream: 6 different weight matrices (944 MB >> L2) launched round-robin, so every launch
-    streams its weights from HBM."""
+def dominant_kernel_roofline(eng, hbm_peak, peak_src, S, guidance, B):
+    """The dominant kernel is bd_stream_kernel: ONE launch = one DiffHead.sample() = S+1 evaluations of the 1.76 B-parameter
+    head + the SDE updates (87 % of an AR step's bytes). Timed live with CUDA events on the launching (current) stream.
+    Algorithmic bytes per launch: (S+1) * 2 * (P_head - P_cond) + 2 * P_cond — every weight streamed
+    once per evaluation, cond_embed once per launch. `traffic` is dram__bytes_read + dram__bytes_write of the same launch
+    from the committed ncu --set full capture (profiles/r01_stream_kernel_ncu.json), or null when that file is absent.
+    `gemm_chain`: the same kernel on a bare chain of 157 MB GEMM ops (M=128, N=15360, K=5120, 4 different weight buffers
+    = 629 MB >> L2) — the steady-state streaming rate without the head's row / attention ops."""
     import torch
     from bitdance_b200 import ops
-    D = eng.head.cfg["D"]
+    head = eng.head
+    D, Dz = head.cfg["D"], head.cfg["Dz"]
     dev = eng.device
-    g = torch.Generator(device=dev)
-    g.manual_seed(123)
-    raw = [(torch.randn((3 * D, D), generator=g, device=dev) * 0.02).to(torch.bfloat16) for _ in range(6)]
-    a = torch.randn(128, D, device=dev).to(torch.bfloat16)
-    out = torch.empty(128, 3 * D, dtype=torch.bfloat16, device=dev)
+    pn = eng.pn
+    R = (2 if guidance > 1.0 else 1) * B
+    z = torch.randn(R, pn, Dz, device=dev)
+    stream_path = head.w_stream is not None and R * pn <= 128
 
-    def time_set(ws, reps=10):
-        for w in ws:
-            ops.gemm(a, w, out=out)
+    def timed(fn, reps):
+        fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            for w in ws:
-                ops.gemm(a, w, out=out)
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / (reps * len(ws))
+        return e0.elapsed_time(e1) / reps
 
-    ms_rowmajor = time_set(raw)
-    packed = [ops.pack_weight(w) for w in raw]
-    del raw
-    ms = time_set(packed)
-    bytes_alg = (3 * D * D + 128 * D + 128 * 3 * D) * 2
+    ms = timed(lambda: head.sample(z, guidance, S), 3)
+    bytes_alg = (S + 1) * 2 * (P_HEAD - P_COND) + 2 * P_COND
     ach = bytes_alg / 1e9 / (ms / 1e3)
-    return {"bound": "hbm", "kernel": "bd_gemm_kernel<128> M=128 N=%d K=%d (tile-major W)" % (3 * D, D), "achieved": ach,
-            "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-            "us_per_launch": ms * 1e3, "algorithmic_bytes_per_launch": bytes_alg,
-            "rowmajor_w_gbs": bytes_alg / 1e9 / (ms_rowmajor / 1e3)}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_stream_kernel_ncu.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {"bound": "hbm",
+           "kernel": ("bd_stream_kernel (persistent: one launch = DiffHead.sample, %d evaluations)" % (S + 1)) if stream_path
+           else "bd_head_sample multi-kernel path (batch > one 128-row tile)",
+           "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak,
+           "traffic": traffic, "ms_per_launch": ms, "us_per_evaluation": ms * 1e3 / (S + 1),
+           "algorithmic_bytes_per_launch": bytes_alg}
+    if stream_path:
+        N, K, nbuf = 3 * D, D, 4
+        w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
+        p0 = ops.stream_pack_weight(w, None)
+        n = p0.data.numel()
+        big = p0.data.repeat(nbuf)
+        views = [ops.StreamWeight(big[i * n:(i + 1) * n], p0.bias, N, K, 1, p0.n_ctas, 0) for i in range(nbuf)]
+        a = ops.to_blocked(torch.randn(128, K, device=dev).to(torch.bfloat16))
+        reps = 8
+        msg = timed(lambda: ops.stream_gemm(a, views, epi="bias", repeat=reps, a_is_blocked=True, M=128), 2)
+        per_op_us = msg * 1e3 / (reps * nbuf)
+        out["gemm_chain"] = {"shape": "M=128 N=%d K=%d, %d ops per launch" % (N, K, reps * nbuf), "us_per_op": per_op_us,
+                             "achieved_gbs": N * K * 2 / 1e9 / (per_op_us / 1e6),
+                             "frac": N * K * 2 / 1e9 / (per_op_us / 1e6) / hbm_peak}
+        del big, views, p0, w
+    return out
 
 
 if __name__ == "__main__":

@@ -43,8 +43,12 @@ __device__ __forceinline__ void epi_apply_store(const GemmEpi& e, const float (&
     __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
     for (int j = 0; j < 8; ++j) p2[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-    reinterpret_cast<uint4*>(o)[0] = pk[0];
-    reinterpret_cast<uint4*>(o)[1] = pk[1];
+    if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+      st_global_32B(o, pk[0], pk[1]);
+    } else {
+      reinterpret_cast<uint4*>(o)[0] = pk[0];
+      reinterpret_cast<uint4*>(o)[1] = pk[1];
+    }
     return;
   }
   float y[32];
@@ -139,7 +143,16 @@ __device__ __forceinline__ void epi_apply_store(const GemmEpi& e, const float (&
   const bool full = (n0 + 32 <= N);
   if (e.out_f32) {
     float* o = reinterpret_cast<float*>(e.out) + static_cast<long long>(m) * e.ld_out + n0;
-    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+    if (full && ((reinterpret_cast<uintptr_t>(o) & 31) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // whole 32-byte sectors (see st_global_32B)
+        const uint4 lo = make_uint4(__float_as_uint(y[8 * j]), __float_as_uint(y[8 * j + 1]), __float_as_uint(y[8 * j + 2]),
+                                    __float_as_uint(y[8 * j + 3]));
+        const uint4 hi = make_uint4(__float_as_uint(y[8 * j + 4]), __float_as_uint(y[8 * j + 5]), __float_as_uint(y[8 * j + 6]),
+                                    __float_as_uint(y[8 * j + 7]));
+        st_global_32B(o + 8 * j, lo, hi);
+      }
+    } else if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
     } else {
@@ -153,8 +166,13 @@ __device__ __forceinline__ void epi_apply_store(const GemmEpi& e, const float (&
       __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
       for (int j = 0; j < 16; ++j) p2[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+      if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {  // whole 32-byte sectors (see st_global_32B)
+        st_global_32B(o, pk[0], pk[1]);
+        st_global_32B(o + 16, pk[2], pk[3]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(o)[j] = pk[j];
+        for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(o)[j] = pk[j];
+      }
     } else {
       for (int j = 0; j < 32; ++j)
         if (n0 + j < N) o[j] = __float2bfloat16_rn(y[j]);
@@ -312,7 +330,16 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (m < M && nc < N) {
         if (splits > 1) {
           float* p = partial + (static_cast<long long>(blockIdx.z) * M + m) * N + nc;
-          if (nc + 32 <= N && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+          if (nc + 32 <= N && ((reinterpret_cast<uintptr_t>(p) & 31) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // whole 32-byte sectors (see st_global_32B)
+              const uint4 lo = make_uint4(__float_as_uint(acc[8 * j]), __float_as_uint(acc[8 * j + 1]),
+                                          __float_as_uint(acc[8 * j + 2]), __float_as_uint(acc[8 * j + 3]));
+              const uint4 hi = make_uint4(__float_as_uint(acc[8 * j + 4]), __float_as_uint(acc[8 * j + 5]),
+                                          __float_as_uint(acc[8 * j + 6]), __float_as_uint(acc[8 * j + 7]));
+              st_global_32B(p + 8 * j, lo, hi);
+            }
+          } else if (nc + 32 <= N && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               reinterpret_cast<float4*>(p)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);

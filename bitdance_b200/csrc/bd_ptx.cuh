@@ -177,6 +177,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// One whole 32-byte sector per store. Measured on B200 (profiles/r01_stream_timeline.txt): 16-byte stores from 128 threads
+// to 128 different rows are partial-sector writes the L2 turns into read-modify-write — an 11.8 us epilogue for a
+// 128 x 112 bf16 tile became 2.1 us with 32-byte stores.
+__device__ __forceinline__ void st_global_32B(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // small numeric helpers shared by the epilogues (rounding points mirror torch autocast semantics)
 // ---------------------------------------------------------------------------------------------

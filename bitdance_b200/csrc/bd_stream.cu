@@ -8,12 +8,6 @@ namespace bd {
 // ---------------------------------------------------------------------------------------------------------------------
 // GEMM-pass epilogues: NC (32 or 16) consecutive accumulator columns of token row m, packed column n
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_global_32B(void* p, const uint4& a, const uint4& b) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
-               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-               : "memory");
-}
-
 // Stores are always whole 32-byte sectors where the tile allows it: 16-byte stores from 128 threads to 128 different rows
 // are partial-sector writes the L2 has to read-modify-write (measured: 11.8 us vs 2.1 us for a 128 x 112 bf16 tile).
 __device__ __forceinline__ void store_bf16x16(uint8_t* outb, const StreamOp& op, int m, int col, const float (&y0)[8],
@@ -191,7 +185,7 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
     }
     case kRowSiluAdd: {  // y = bf16(silu(bf16(temb[it] + cemb[r])))   (TransEncoder.forward :330)
       if (r >= M) return;
-      const __nv_bfloat16* te = reinterpret_cast<const __nv_bfloat16*>(op.p0) + static_cast<long long>(it) * op.N;
+      const __nv_bfloat16* te = reinterpret_cast<const __nv_bfloat16*>(op.p0) + static_cast<long long>(it + op.i0) * op.N;
       const __nv_bfloat16* ce = reinterpret_cast<const __nv_bfloat16*>(op.p1) + static_cast<long long>(r) * op.N;
       uint8_t* dst = reinterpret_cast<uint8_t*>(op.o0);
       for (int c = tid; c < op.N / 8; c += 128) {
@@ -503,6 +497,11 @@ struct RingPos {  // position in a ring of n slots: slot index + how many times 
   }
 };
 
+// wait_prev: 1 = all earlier ops, 0 = none, -k = all earlier ops except the k most recent ones
+__device__ __forceinline__ unsigned int wait_target(int wait_prev, int q, int G) {
+  return static_cast<unsigned int>(G) * static_cast<unsigned int>(wait_prev < 0 ? max(q + wait_prev, 0) : q);
+}
+
 __device__ __forceinline__ void op_at(const StreamProgram& prog, int q, int& idx, int& it) {
   if (q < prog.n_pre) {
     idx = q;
@@ -575,6 +574,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         op_at(prog, q, idx, it);
         const StreamOp& op = prog.ops[idx];
         if (op.kind != kOpGemm) continue;
+        if ((op.flags & kFlagSkipLast) && it == prog.n_iter - 1) continue;
         const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
         if (part.units == 0) continue;
         const int nsteps = stream_steps(part.kbs);
@@ -607,10 +607,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         op_at(prog, q, idx, it);
         const StreamOp& op = prog.ops[idx];
         if (op.kind != kOpGemm) continue;
+        if ((op.flags & kFlagSkipLast) && it == prog.n_iter - 1) continue;
         const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
         if (part.units == 0) continue;
         if (op.wait_prev) {
-          grid_wait(prog.sync, static_cast<unsigned int>(G) * static_cast<unsigned int>(q));
+          grid_wait(prog.sync, wait_target(op.wait_prev, q, G));
           fence_proxy_async_all();  // other CTAs' generic-proxy stores -> this thread's async-proxy (bulk copy) reads
         }
         BD_STAMP(q, 0);
@@ -643,6 +644,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         op_at(prog, q, idx, it);
         const StreamOp& op = prog.ops[idx];
         if (op.kind != kOpGemm) continue;
+        if ((op.flags & kFlagSkipLast) && it == prog.n_iter - 1) continue;
         const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
         if (part.units == 0) continue;
         for (int i = 0; i < part.npass; ++i) {
@@ -695,14 +697,26 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
       op_at(prog, q, idx, it);
       // by value: the descriptor lives in registers for the whole op. (Reading it through the kernel-parameter bank with a
       // run-time index inside the per-element epilogue loops cost ~3 us per 32-column chunk: measured 11 us -> 1 us.)
-      const StreamOp op = prog.ops[idx];
-      if (op.kind == kOpGemm) {
+      StreamOp op = prog.ops[idx];
+      const bool skipped = (op.flags & kFlagSkipLast) && it == prog.n_iter - 1;
+      if ((op.flags & kFlagParityIt) ? (it & 1) : ((op.flags & kFlagParityNext) ? ((it + 1) & 1) : 0)) {
+        if (op.kind == kOpGemm) {
+          op.o0 = reinterpret_cast<uint8_t*>(op.o0) + op.l1;  // double-buffered GEMM output
+        } else {  // double-buffered modulation operands of the row ops
+          op.p3 = reinterpret_cast<const uint8_t*>(op.p3) + op.l1;
+          op.p4 = reinterpret_cast<const uint8_t*>(op.p4) + op.l1;
+          op.p6 = reinterpret_cast<const uint8_t*>(op.p6) + op.l1;
+        }
+      }
+      if (skipped) {
+        // nothing to do, but the arrival below keeps the cumulative barrier count in step
+      } else if (op.kind == kOpGemm) {
         const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
         const int rows = op.i1 > 0 ? op.i1 : prog.M;  // valid token rows of this op
         if (part.units == 0 && op.wait_prev) {
           // a CTA without work must not run ahead: the arrival counter is cumulative, so every CTA has to pass every
           // dependency (CTAs with work do so through their A producer -> MMA -> accumulator chain)
-          if (tid == 0) grid_wait(prog.sync, static_cast<unsigned int>(G) * static_cast<unsigned int>(q));
+          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, q, G));
           epi_bar();
         }
         for (int i = 0; i < part.npass; ++i) {
@@ -749,7 +763,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         }
       } else {
         if (op.wait_prev) {
-          if (tid == 0) grid_wait(prog.sync, static_cast<unsigned int>(G) * static_cast<unsigned int>(q));
+          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, q, G));
           epi_bar();
         }
         if (op.kind == kOpRow) {
@@ -832,6 +846,8 @@ static unsigned long long* g_stream_dbg = nullptr;
 static int g_stream_dbg_ops = 0;
 static int g_stream_dbg_mode = 0;
 static int g_stream_w_slots = kStreamWSlotsDefault, g_stream_a_slots = kStreamASlotsDefault;
+
+int stream_tuning_mode() { return g_stream_dbg_mode; }
 
 int stream_launch(const StreamProgram& prog_in, cudaStream_t stream) {
   static thread_local StreamProgram prog;

@@ -38,6 +38,7 @@ constexpr int kStreamMaxOps = 128;
 constexpr int kStreamMaxIter = 104;
 
 enum : int { kOpGemm = 0, kOpRow = 1, kOpAttn = 2 };
+enum : int { kFlagBlocked = 1, kFlagParityIt = 2, kFlagParityNext = 4, kFlagSkipLast = 8 };
 enum : int { kEpiBias = 0, kEpiSwiglu8 = 1, kEpiPartial = 2 };
 enum : int {
   kRowCastCond = 0,   // fp32 [M, K] -> blocked bf16
@@ -53,6 +54,10 @@ enum : int {
 // One op. Field meaning per kind:
 //  GEMM: p0 = W stream-packed, p1 = A blocked, p2 = bias (packed order), o0 = out, l0 = ld_out (elements), N, K, ksplit,
 //        sub = epilogue kind, act, flags bit0 = out is blocked bf16 (else row-major), i1 = valid rows (0: prog.M)
+//  flags bit1 / bit2: double-buffered operand — add l1 bytes to o0 (GEMM) or to p3, p4, p6 (ROW) when the iteration `it`
+//        (bit1) or `it + 1` (bit2) is odd; flags bit3: the op is skipped in the last iteration (it prepares the next one).
+//  wait_prev = 0 on a GEMM makes it a FILLER: its operands were complete long before, so its weight stream and MMAs
+//        overlap the epilogue / row op / barrier of the ops around it (the head's adaLN GEMM of the next evaluation).
 //  ROW:  sub = row kind; pointers documented at each row function
 //  ATTN: p0 = qkv row-major bf16 [M, 3D], o0 = out blocked bf16, N = D, K = head_dim
 struct StreamOp {
@@ -143,6 +148,7 @@ __host__ __device__ inline long long blk_off(int row, int col) {
 
 struct StreamProgram;
 int stream_launch(const StreamProgram& prog, cudaStream_t stream);  // bd_stream.cu
+int stream_tuning_mode();                                           // bd_stream_set_tuning's mode bits
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------------
