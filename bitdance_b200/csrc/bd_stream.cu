@@ -29,7 +29,7 @@ __device__ __forceinline__ void store_bf16x8(uint8_t* outb, const StreamOp& op, 
 
 template <int NC>
 __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m, int n, const float (&acc)[NC],
-                                               int split, int mode) {
+                                               int split, int mode, const __nv_bfloat16* bias_sm) {
   if (m >= M) return;
   if (mode & 2) {  // experiment: no stores (keep the data dependency alive)
     float t = 0.f;
@@ -52,12 +52,11 @@ __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m,
     return;
   }
   float b[NC];
-  if (op.p2 && !(mode & 1)) {
-    const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(op.p2) + n;
+  if (bias_sm && !(mode & 1)) {  // this pass's bias slice, staged in shared memory before the accumulator was ready
 #pragma unroll
     for (int j = 0; j < NC / 8; ++j) {
       float t[8];
-      bf16x8_to_f(*reinterpret_cast<const uint4*>(bp + 8 * j), t);
+      bf16x8_to_f(*reinterpret_cast<const uint4*>(bias_sm + 8 * j), t);
 #pragma unroll
       for (int i = 0; i < 8; ++i) b[8 * j + i] = t[i];
     }
@@ -483,7 +482,8 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
 struct StreamSmem {
   static constexpr int kRing = kStreamSlots * kStepBytes;
   static constexpr int kBars = (2 * kStreamSlots + 4) * 8;
-  static constexpr int kTotal = kRing + kBars + 64 /*tmem slot + red*/ + 1024 /*align slack*/;
+  static constexpr int kBias = 2 * 256;  // one pass's bias slice (<= 128 bf16) per accumulator buffer
+  static constexpr int kTotal = kRing + kBars + 64 /*tmem slot + red*/ + kBias + 1024 /*align slack*/;
 };
 
 struct RingPos {  // position in a ring of n slots: slot index + how many times the ring wrapped
@@ -494,6 +494,72 @@ struct RingPos {  // position in a ring of n slots: slot index + how many times 
       slot = 0;
       ++round;
     }
+  }
+};
+
+// The weight stream of one CTA as a flat sequence of steps (op after op, pass after pass, k rotation inside a pass): two
+// cursors walk it — the L2 prefetch cursor a fixed distance ahead of the shared-memory load cursor.
+struct WStream {
+  const StreamProgram& prog;
+  int G, c, total;
+  int q = -1, i = 0, t = 0;           // op sequence number, pass, step
+  int npass = 0, nsteps = 0, rot = 0, kbs = 0, N = 0;
+  StreamPart part{};
+  const uint8_t* w = nullptr;
+  const uint8_t* base = nullptr;      // first slot of the current pass
+  uint32_t kb_bytes = 0;
+  __device__ WStream(const StreamProgram& p, int G_, int c_, int total_) : prog(p), G(G_), c(c_), total(total_) {}
+  __device__ __forceinline__ bool next_op() {
+    for (++q; q < total; ++q) {
+      int idx, it;
+      if (q < prog.n_pre) { idx = q; it = 0; }
+      else {
+        const int b = q - prog.n_pre, nb = prog.n_body * prog.n_iter;
+        if (b < nb) { it = b / prog.n_body; idx = prog.n_pre + b % prog.n_body; }
+        else { idx = prog.n_pre + prog.n_body + (b - nb); it = prog.n_iter - 1; }
+      }
+      const StreamOp& op = prog.ops[idx];
+      if (op.kind != kOpGemm) continue;
+      if ((op.flags & kFlagSkipLast) && it == prog.n_iter - 1) continue;
+      part = stream_partition(op.N, op.K, op.ksplit, G, c);
+      if (part.units == 0) continue;
+      N = op.N;
+      w = reinterpret_cast<const uint8_t*>(op.p0);
+      npass = part.npass;
+      kbs = part.kbs;
+      nsteps = stream_steps(part.kbs);
+      rot = stream_k_rot(c, nsteps);
+      i = 0;
+      t = 0;
+      set_pass();
+      return true;
+    }
+    return false;
+  }
+  __device__ __forceinline__ void set_pass() {
+    const int wd = (stream_pass_u0(part, i + 1) - stream_pass_u0(part, i)) * 16;
+    kb_bytes = static_cast<uint32_t>(wd) * 128u;
+    base = w + stream_pass_offset(N, part, i) * 2048;
+  }
+  // address / size of the next step; false at the end of the program
+  __device__ __forceinline__ bool next(const uint8_t*& addr, uint32_t& bytes) {
+    if (q < 0 || t >= nsteps) {
+      if (q >= 0 && i + 1 < npass) {
+        ++i;
+        t = 0;
+        set_pass();
+      } else if (!next_op()) {
+        return false;
+      }
+    }
+    int st = rot + t;
+    if (st >= nsteps) st -= nsteps;
+    const int kbl = st * kKbPerStep;
+    const int nkb = min(kKbPerStep, kbs - kbl);
+    bytes = kb_bytes * static_cast<uint32_t>(nkb);  // the k-blocks of a pass are adjacent in HBM
+    addr = base + static_cast<long long>(kbl) * kb_bytes;
+    ++t;
+    return true;
   }
 };
 
@@ -538,6 +604,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);
+  __nv_bfloat16* bias_s = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(tmem_slot) + 64);
 
   const int warp = threadIdx.x >> 5;
   const int c = blockIdx.x;
@@ -569,33 +636,29 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
     // ===================== W producer: runs ahead of every dependency =====================
     if (elect_one()) {
       RingPos wr(kStreamWSlots);
-      for (int q = 0; q < total; ++q) {
-        int idx, it;
-        op_at(prog, q, idx, it);
-        const StreamOp& op = prog.ops[idx];
-        if (op.kind != kOpGemm) continue;
-        if ((op.flags & kFlagSkipLast) && it == prog.n_iter - 1) continue;
-        const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
-        if (part.units == 0) continue;
-        const int nsteps = stream_steps(part.kbs);
-        const int rot = stream_k_rot(c, nsteps);
-        for (int i = 0; i < part.npass; ++i) {
-          const int w = (stream_pass_u0(part, i + 1) - stream_pass_u0(part, i)) * 16;
-          const uint32_t kb_bytes = static_cast<uint32_t>(w) * 128u;
-          const uint8_t* base = reinterpret_cast<const uint8_t*>(op.p0) + stream_pass_offset(op.N, part, i) * 2048;
-          for (int t = 0; t < nsteps; ++t) {
-            int st = rot + t;
-            if (st >= nsteps) st -= nsteps;
-            const int kbl = st * kKbPerStep;
-            const int nkb = min(kKbPerStep, part.kbs - kbl);
-            const uint32_t bytes = kb_bytes * static_cast<uint32_t>(nkb);  // the k-blocks of a pass are adjacent in HBM
-            const uint32_t s = wr.slot;
-            if (wr.round > 0) mbar_wait(&empty_w[s], (wr.round & 1u) ^ 1u);
-            mbar_expect_tx(&full_w[s], bytes);
-            bulk_g2s(smem_w + s * kStepBytes, base + static_cast<long long>(kbl) * kb_bytes, bytes, &full_w[s], kEvictFirst);
-            wr.advance();
-          }
+      WStream ld(prog, G, c, total), pf(prog, G, c, total);
+      const uint8_t* addr;
+      uint32_t bytes;
+      // L2 prefetch cursor: `pf_steps` steps (~28 KB each) ahead of the load cursor. When the ring is full and this thread
+      // blocks — the other warps are in an epilogue, a row op or a grid barrier — HBM keeps streaming the next weights into
+      // L2 (148 CTAs x pf_steps x 28 KB, well inside the 126 MB), and the ring then refills from L2 faster than from HBM.
+      bool pf_live = prog.pf_steps > 0;
+      for (int k = 0; pf_live && k < prog.pf_steps; ++k) {
+        pf_live = pf.next(addr, bytes);
+        if (pf_live) bulk_prefetch_l2(addr, bytes);
+      }
+      while (ld.next(addr, bytes)) {
+        if (pf_live) {
+          const uint8_t* pa;
+          uint32_t pb;
+          pf_live = pf.next(pa, pb);
+          if (pf_live) bulk_prefetch_l2(pa, pb);
         }
+        const uint32_t s = wr.slot;
+        if (wr.round > 0) mbar_wait(&empty_w[s], (wr.round & 1u) ^ 1u);
+        mbar_expect_tx(&full_w[s], bytes);
+        bulk_g2s(smem_w + s * kStepBytes, addr, bytes, &full_w[s], kEvictFirst);
+        wr.advance();
       }
     }
   } else if (warp == 2) {
@@ -724,6 +787,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           const int w = (stream_pass_u0(part, i + 1) - u0) * 16;
           const int n0 = (part.unit0 + u0) * 16;
           const uint32_t buf = pi & 1u;
+          // bias slice of this pass -> shared memory while the MMAs are still running (a global load per chunk after the
+          // accumulator is ready would put an L2 round trip — there is no L1 left — on the dependency path)
+          const __nv_bfloat16* bias_sm = nullptr;
+          if (op.p2 && op.sub != kEpiPartial) {
+            if (tid < w / 8)
+              reinterpret_cast<uint4*>(bias_s + buf * 128)[tid] =
+                  *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(op.p2) + n0 + tid * 8);
+            epi_bar();
+            bias_sm = bias_s + buf * 128;
+          }
           mbar_wait(&acc_full[buf], (pi >> 1) & 1u);
           tc_fence_after();
           if (tid == 0 && i == part.npass - 1) BD_STAMP(q, 3);
@@ -738,7 +811,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
             float acc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-            gemm_epi_chunk<16>(op, rows, m, n0 + cc, acc, part.split, prog.dbg_mode);
+            gemm_epi_chunk<16>(op, rows, m, n0 + cc, acc, part.split, prog.dbg_mode, bias_sm ? bias_sm + cc : nullptr);
           };
           if ((n0 & 31) != 0) {
             chunk16(0);
@@ -752,7 +825,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
             float acc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-            gemm_epi_chunk<32>(op, rows, m, n0 + col, acc, part.split, prog.dbg_mode);
+            gemm_epi_chunk<32>(op, rows, m, n0 + col, acc, part.split, prog.dbg_mode, bias_sm ? bias_sm + col : nullptr);
             if (tid == 0 && i == part.npass - 1 && col <= 16) BD_STAMP(q, 7);
           }
           if (col < w) chunk16(col);
@@ -845,6 +918,7 @@ __global__ void __launch_bounds__(256) stream_pack_kernel(const __nv_bfloat16* _
 static unsigned long long* g_stream_dbg = nullptr;
 static int g_stream_dbg_ops = 0;
 static int g_stream_dbg_mode = 0;
+static int g_stream_pf_steps = 0;
 static int g_stream_w_slots = kStreamWSlotsDefault, g_stream_a_slots = kStreamASlotsDefault;
 
 int stream_tuning_mode() { return g_stream_dbg_mode; }
@@ -855,6 +929,7 @@ int stream_launch(const StreamProgram& prog_in, cudaStream_t stream) {
   prog.dbg = g_stream_dbg;
   prog.dbg_ops = g_stream_dbg_ops;
   prog.dbg_mode = g_stream_dbg_mode;
+  prog.pf_steps = g_stream_pf_steps;
   if (prog.w_slots <= 0 || prog.a_slots <= 0 || prog.w_slots + prog.a_slots > kStreamSlots) {
     prog.w_slots = g_stream_w_slots;
     prog.a_slots = g_stream_a_slots;
@@ -891,6 +966,18 @@ int bd_stream_num_ctas(void) { return num_sms(); }
 int bd_stream_set_debug(void* buf, int max_ops) {
   g_stream_dbg = static_cast<unsigned long long*>(buf);
   g_stream_dbg_ops = buf ? max_ops : 0;
+  return BD_OK;
+}
+
+int bd_stream_set_ksplit(int ksplit) {  // before packing any weights: the packer and the program builder must agree
+  BD_REQUIRE(ksplit == 1 || ksplit == 2 || ksplit == 4);
+  stream_ksplit_small() = ksplit;
+  return BD_OK;
+}
+
+int bd_stream_set_prefetch(int steps) {
+  BD_REQUIRE(steps >= 0 && steps <= 256);
+  g_stream_pf_steps = steps;
   return BD_OK;
 }
 

@@ -90,6 +90,7 @@ struct StreamProgram {
   int dbg_ops;
   int dbg_mode;   // experiment switches (bd_stream_set_debug): bit0 no bias loads, bit1 no stores, bit2 32-byte stores
   int w_slots, a_slots;  // ring split, w_slots + a_slots <= kStreamSlots (0: defaults)
+  int pf_steps;          // L2 prefetch distance of the weight stream, in ring steps (0: off)
   float sched[kStreamMaxIter][6];  // per iteration: t, dt, denom, var, 1-t, noise_scale   (sampling_x.py:62-68)
   StreamOp ops[kStreamMaxOps];
 };
@@ -106,9 +107,14 @@ struct StreamPart {
   int npass;    // passes of <= 8 units (128 weight rows)
 };
 
-__host__ __device__ inline int stream_ksplit_for(int N, int K, int G) {
-  const int U = N / 16, KB = (K + 63) / 64;
-  if (U < 4 * G && (KB % 4) == 0 && KB >= 16) return 4;
+// k-split of a Linear whose N is small next to the CTA count (its output then goes through fp32 partials + a row op)
+inline int& stream_ksplit_small() {
+  static int v = 4;
+  return v;
+}
+inline int stream_ksplit_for(int N, int K, int G) {
+  const int U = N / 16, KB = (K + 63) / 64, S = stream_ksplit_small();
+  if (U < 4 * G && (KB % S) == 0 && KB >= 16) return S;
   return 1;
 }
 
@@ -165,6 +171,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {

@@ -277,6 +277,11 @@ int bd_stream_set_debug(void* buf, int max_ops);
  * activations (default 5 + 2; the activation ring needs >= 2 slots, it also hosts the attention tiles), and epilogue
  * experiment switches (0 = product behaviour; bit0 no bias loads, bit1 no stores — measurement only, results are wrong) */
 int bd_stream_set_tuning(int w_slots, int a_slots, int mode);
+/* L2 prefetch distance of the weight stream in ring steps of ~28 KB per CTA (0 = off): the producer warp issues
+ * cp.async.bulk.prefetch.L2 that far ahead of its shared-memory loads, so HBM keeps streaming while the ring is full. */
+int bd_stream_set_prefetch(int steps);
+/* k-split (1, 2 or 4; default 4) bd_stream_ksplit returns for small-N Linears. Set BEFORE packing weights. */
+int bd_stream_set_ksplit(int ksplit);
 /* k-split the engine uses for a Linear whose output goes through fp32 partials (N small next to the SM count) */
 int bd_stream_ksplit(int N, int K, int n_ctas);
 size_t bd_stream_packed_elems(int N, int K); /* bf16 elements of a stream-packed [N, K] weight (K padded to 64) */
