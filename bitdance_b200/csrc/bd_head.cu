@@ -353,7 +353,7 @@ static HeadStreamWs head_stream_ws_layout(const bd_head_weights_t& w, int S) {
   L.y = take(blocked_bytes(w.D));
   L.mod = take(128 * n_mod * 2);
   L.a = take(blocked_bytes(w.D));
-  L.qkv = take(128 * 3 * D * 2);
+  L.qkv = take(blocked_bytes(3 * w.D));  // blocked: the attention op fetches its Q / K / V tiles by bulk copy
   L.o = take(blocked_bytes(w.D));
   L.g = take(blocked_bytes(w.hidden));
   L.cemb = take(128 * D * 2);
@@ -479,7 +479,7 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
   for (int blk = 0; blk < w.n_blocks; ++blk) {
     const bd_head_block_t& bw = w.blocks[blk];
     const __nv_bfloat16* md = mod + static_cast<long long>(blk / switch_freq) * 6 * D;
-    gemm_op(bw.wqkv_w, base + L.a, bw.wqkv_b, 3 * D, D, 1, kEpiBias, kActNone, base + L.qkv, 3 * D, false);
+    gemm_op(bw.wqkv_w, base + L.a, bw.wqkv_b, 3 * D, D, 1, kEpiBias, kActNone, base + L.qkv, 0, true);
     {
       StreamOp& op = prog.ops[n++];
       op = StreamOp{};

@@ -362,28 +362,47 @@ __device__ __forceinline__ uint32_t s_pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-template <int HD>
-__device__ __forceinline__ uint32_t s_tile_off(int row, int chunk) {
-  return static_cast<uint32_t>(row * (HD * 2) + ((chunk ^ (row & 7)) << 4));
+// A Q / K / V / O tile in shared memory: HD/64 half-tiles of [64 rows x 128 B], each the verbatim image of `pn` rows of one
+// k-block of a blocked activation (so a tile is filled by HD/64 bulk copies and written back sector by sector). The
+// 128-byte swizzle of a blocked buffer uses the row index inside its 128-row block, hence row0 = seq * pn.
+__device__ __forceinline__ uint32_t s_tile_off(int row, int chunk, int row0) {
+  return static_cast<uint32_t>((chunk >> 3) * 8192 + row * 128 + (((chunk & 7) ^ ((row0 + row) & 7)) << 4));
 }
 
+// Attention over the pn <= 64 tokens of one (sequence, head). qkv is the blocked bf16 output of the wqkv GEMM
+// ([3D/64][128][64]); the tiles arrive by bulk copy (one mbarrier round trip instead of a chain of 16-byte loads through
+// the L1-less load path: measured 12.5 us -> see profiles), the output goes back as whole 32-byte sectors.
 template <int HD>
-__device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid, uint8_t* smem) {
+__device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid, uint8_t* smem, uint64_t* aux_bar,
+                                          uint32_t aux_parity) {
   const int D = op.N, pn = op.i0, H = D / HD;
   const int seq = unit / H, hd = unit % H;
+  const int row0 = seq * pn;
+  constexpr int kHalves = HD / 64;
+  constexpr int kTile = kHalves * 8192;
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + 64 * HD * 2;
-  uint8_t* sV = sK + 64 * HD * 2;
-  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(op.p0);
-  constexpr int kChunks = HD / 8;
-  for (int i = tid; i < 3 * 64 * kChunks; i += 128) {
-    const int which = i / (64 * kChunks), rem = i % (64 * kChunks);
-    const int rr = rem / kChunks, c = rem % kChunks;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (rr < pn)
-      v = ldcg_u4(qkv + (static_cast<long long>(seq) * pn + rr) * 3 * D + which * D + hd * HD + c * 8);
-    *reinterpret_cast<uint4*>(smem + which * (64 * HD * 2) + s_tile_off<HD>(rr, c)) = v;
+  uint8_t* sK = smem + kTile;
+  uint8_t* sV = sK + kTile;
+  const uint8_t* qkv = reinterpret_cast<const uint8_t*>(op.p0);
+  if (tid == 0) {
+    fence_proxy_async_all();  // the wqkv epilogues' generic-proxy stores (acquired by this thread) -> bulk-copy reads
+    mbar_expect_tx(aux_bar, static_cast<uint32_t>(3 * kHalves * pn * 128));
+#pragma unroll
+    for (int which = 0; which < 3; ++which)
+#pragma unroll
+      for (int hf = 0; hf < kHalves; ++hf) {
+        const int kb = (which * D + hd * HD) / 64 + hf;
+        bulk_g2s(smem + which * kTile + hf * 8192, qkv + static_cast<long long>(kb) * kSlotBytes + row0 * 128,
+                 static_cast<uint32_t>(pn * 128), aux_bar, kEvictLast);
+      }
   }
+  if (pn < 64) {  // rows beyond pn: V must be finite (P is exactly 0 there), K / Q rows are masked / never stored
+    for (int i = tid; i < (64 - pn) * 8 * kHalves; i += 128) {
+      const int hf = i / ((64 - pn) * 8), rem = i % ((64 - pn) * 8);
+      *reinterpret_cast<uint4*>(sV + hf * 8192 + (pn + rem / 8) * 128 + (rem % 8) * 16) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  mbar_wait(aux_bar, aux_parity);
   epi_bar();
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -396,12 +415,12 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
 #pragma unroll
   for (int ks = 0; ks < HD / 16; ks += 2) {
     uint32_t a0[4], a1[4];
-    s_ldmatrix_x4(a0, smem_u32(sQ + s_tile_off<HD>(warp * 16 + (lane & 15), 2 * ks + (lane >> 4))));
-    s_ldmatrix_x4(a1, smem_u32(sQ + s_tile_off<HD>(warp * 16 + (lane & 15), 2 * ks + 2 + (lane >> 4))));
+    s_ldmatrix_x4(a0, smem_u32(sQ + s_tile_off(warp * 16 + (lane & 15), 2 * ks + (lane >> 4), row0)));
+    s_ldmatrix_x4(a1, smem_u32(sQ + s_tile_off(warp * 16 + (lane & 15), 2 * ks + 2 + (lane >> 4), row0)));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint32_t bk[4];
-      s_ldmatrix_x4(bk, smem_u32(sK + s_tile_off<HD>(8 * j + (lane & 7), 2 * ks + (lane >> 3))));
+      s_ldmatrix_x4(bk, smem_u32(sK + s_tile_off(8 * j + (lane & 7), 2 * ks + (lane >> 3), row0)));
       s_mma_16816(s[j], a0, bk[0], bk[1]);
       s_mma_16816(s[j], a1, bk[2], bk[3]);
     }
@@ -450,7 +469,7 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
 #pragma unroll
     for (int n = 0; n < HD / 8; n += 2) {
       uint32_t bv[4];
-      s_ldmatrix_x4_trans(bv, smem_u32(sV + s_tile_off<HD>(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), n + (lane >> 4))));
+      s_ldmatrix_x4_trans(bv, smem_u32(sV + s_tile_off(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), n + (lane >> 4), row0)));
       s_mma_16816(o_acc[n], pa[kk], bv[0], bv[1]);
       s_mma_16816(o_acc[n + 1], pa[kk], bv[2], bv[3]);
     }
@@ -460,18 +479,25 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
     l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
     l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
   }
-  uint8_t* out = reinterpret_cast<uint8_t*>(op.o0);
+  // O tile -> the Q tile's place (a warp only ever touches its own 16 rows of Q), then back to HBM as whole sectors
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int qrow = warp * 16 + g + 8 * r;
-    if (qrow >= pn) continue;
     const float inv = l[r] > 0.f ? 1.0f / l[r] : 0.f;
-    const int row = seq * pn + qrow;
 #pragma unroll
-    for (int n = 0; n < HD / 8; ++n) {
-      const uint32_t pk = s_pack_bf16(o_acc[n][2 * r] * inv, o_acc[n][2 * r + 1] * inv);
-      *reinterpret_cast<uint32_t*>(out + blk_off(row, hd * HD + 8 * n + 2 * t)) = pk;
-    }
+    for (int n = 0; n < HD / 8; ++n)
+      *reinterpret_cast<uint32_t*>(sQ + s_tile_off(qrow, n, row0) + 4 * t) =
+          s_pack_bf16(o_acc[n][2 * r] * inv, o_acc[n][2 * r + 1] * inv);
+  }
+  __syncwarp();
+  uint8_t* out = reinterpret_cast<uint8_t*>(op.o0);
+  for (int i = lane; i < 16 * 4 * kHalves; i += 32) {  // 16 rows x (HD / 16) sectors of 32 bytes
+    const int hf = i / 64, rr = (i % 64) / 4, sec = i % 4;
+    const int qrow = warp * 16 + rr;
+    if (qrow >= pn) continue;
+    const uint8_t* src = sQ + hf * 8192 + qrow * 128 + sec * 32;
+    const uint4 a = *reinterpret_cast<const uint4*>(src), b = *reinterpret_cast<const uint4*>(src + 16);
+    st_global_32B(out + static_cast<long long>((hd * HD) / 64 + hf) * kSlotBytes + (row0 + qrow) * 128 + sec * 32, a, b);
   }
   epi_bar();  // tiles (aliasing the A ring) dead
 }
@@ -481,9 +507,11 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
 // ---------------------------------------------------------------------------------------------------------------------
 struct StreamSmem {
   static constexpr int kRing = kStreamSlots * kStepBytes;
-  static constexpr int kBars = (2 * kStreamSlots + 4) * 8;
+  static constexpr int kBars = (2 * kStreamSlots + 4 + 1) * 8;  // rings, accumulators, + the epilogue warps' own bulk-copy barrier
   static constexpr int kBias = 2 * 256;  // one pass's bias slice (<= 128 bf16) per accumulator buffer
-  static constexpr int kTotal = kRing + kBars + 64 /*tmem slot + red*/ + kBias + 1024 /*align slack*/;
+  static constexpr int kMisc = 256;      // barriers (<= 160 B), TMEM slot at +192, reduction scratch at +208
+  static_assert(kBars <= 192, "barrier area");
+  static constexpr int kTotal = kRing + kMisc + kBias + 1024 /*align slack*/;
 };
 
 struct RingPos {  // position in a ring of n slots: slot index + how many times the ring wrapped
@@ -602,9 +630,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
   uint64_t* empty_a = full_a + kStreamASlots;
   uint64_t* acc_full = empty_a + kStreamASlots;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* aux_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + StreamSmem::kRing + 192);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);
-  __nv_bfloat16* bias_s = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(tmem_slot) + 64);
+  __nv_bfloat16* bias_s = reinterpret_cast<__nv_bfloat16*>(smem + StreamSmem::kRing + StreamSmem::kMisc);  // 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int c = blockIdx.x;
@@ -624,6 +653,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
     }
+    mbar_init(aux_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -754,7 +784,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
     const int lane = tid & 31;
     const int qd = warp & 3;
     const int m = qd * 32 + lane;
-    uint32_t pi = 0;
+    uint32_t pi = 0, aux_uses = 0;
     for (int q = 0; q < total; ++q) {
       int idx, it;
       op_at(prog, q, idx, it);
@@ -844,8 +874,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         } else {
           const int units = (prog.M / op.i0) * (op.N / op.K);
           if (c < units) {
-            if (op.K == 128) attn_unit<128>(op, c, tid, smem_a);
-            else attn_unit<64>(op, c, tid, smem_a);
+            if (op.K == 128) attn_unit<128>(op, c, tid, smem_a, aux_bar, aux_uses & 1u);
+            else attn_unit<64>(op, c, tid, smem_a, aux_bar, aux_uses & 1u);
+            ++aux_uses;
           }
         }
         // generic-proxy writes to the A ring (attention tiles / final row) before later async-proxy (bulk copy) writes
