@@ -66,7 +66,7 @@ cmp("tfreq", blocked(ws_s, os_["tfreq"], S + 1, 256), rowmajor(ws_t, ot["tfreq"]
 cmp("th", blocked(ws_s, os_["th"], S + 1, D), rowmajor(ws_t, ot["th"], S + 1, D))
 cmp("y", blocked(ws_s, os_["y"], M, D), rowmajor(ws_t, ot["y"], M, D))
 cmp("mod", rowmajor(ws_s, os_["mod"], M, n_mod), rowmajor(ws_t, ot["mod"], M, n_mod))
-cmp("qkv", rowmajor(ws_s, os_["qkv"], M, 3 * D), rowmajor(ws_t, ot["qkv"], M, 3 * D))
+cmp("qkv", blocked(ws_s, os_["qkv"], M, 3 * D), rowmajor(ws_t, ot["qkv"], M, 3 * D))
 cmp("o", blocked(ws_s, os_["o"], M, D), rowmajor(ws_t, ot["o"], M, D))
 cmp("g", blocked(ws_s, os_["g"], M, hid), rowmajor(ws_t, ot["g"], M, hid))
 cmp("h", rowmajor(ws_s, os_["h"], M, D), rowmajor(ws_t, ot["h"], M, D))

@@ -103,3 +103,21 @@ def test_stream_gemm_chain_of_weights_and_repeat():
     out = ops.stream_gemm(a, views, epi="bias", repeat=5).float()
     ref = _bf(_ref_linear(a, ws[-1], None))
     assert (out - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item() + 1e-3
+
+
+def test_stream_host_policy_cpu():
+    """host-side policy functions of the engine (no GPU): packed size and the small-N k-split rule"""
+    import ctypes as C
+    import __graft_entry__ as ge
+    ge.build()
+    from bitdance_b200 import _lib
+    lib = _lib.load()
+    lib.bd_stream_packed_elems.restype = C.c_size_t
+    assert lib.bd_stream_packed_elems(5120, 5120) == 5120 * 5120
+    assert lib.bd_stream_packed_elems(5120, 32) == 5120 * 64          # K padded to one 64-wide k-block
+    assert lib.bd_stream_packed_elems(5121, 64) == 0                  # N must be a multiple of 16
+    assert lib.bd_stream_ksplit(5120, 5120, 148) == 4                 # wo: 320 units < 4 * 148 CTAs -> 4 k-ranges
+    assert lib.bd_stream_ksplit(5120, 7680, 148) == 4                 # w2
+    assert lib.bd_stream_ksplit(15360, 5120, 148) == 1                # wqkv / w1: enough units
+    assert lib.bd_stream_ksplit(256, 256, 148) == 1                   # tiny models: too few k-blocks to split
+    assert lib.bd_stream_set_tuning(5, 2, 0) == 0 and lib.bd_stream_set_tuning(6, 2, 0) != 0   # 7 ring slots in total
