@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
         if (part.units == 0) continue;
         if (op.wait_prev) {
-          grid_wait(prog.sync, wait_target(op.wait_prev, q, G));
+          grid_wait(prog.sync, wait_target(op.wait_prev, q, G), static_cast<unsigned int>(prog.poll_ns));
           fence_proxy_async_all();  // other CTAs' generic-proxy stores -> this thread's async-proxy (bulk copy) reads
         }
         BD_STAMP(q, 0);
@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         if (part.units == 0 && op.wait_prev) {
           // a CTA without work must not run ahead: the arrival counter is cumulative, so every CTA has to pass every
           // dependency (CTAs with work do so through their A producer -> MMA -> accumulator chain)
-          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, q, G));
+          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, q, G), static_cast<unsigned int>(prog.poll_ns));
           epi_bar();
         }
         for (int i = 0; i < part.npass; ++i) {
@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         }
       } else {
         if (op.wait_prev) {
-          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, q, G));
+          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, q, G), static_cast<unsigned int>(prog.poll_ns));
           epi_bar();
         }
         if (op.kind == kOpRow) {
@@ -950,6 +950,7 @@ static unsigned long long* g_stream_dbg = nullptr;
 static int g_stream_dbg_ops = 0;
 static int g_stream_dbg_mode = 0;
 static int g_stream_pf_steps = 0;
+static int g_stream_poll_ns = 32;
 static int g_stream_w_slots = kStreamWSlotsDefault, g_stream_a_slots = kStreamASlotsDefault;
 
 int stream_tuning_mode() { return g_stream_dbg_mode; }
@@ -961,6 +962,7 @@ int stream_launch(const StreamProgram& prog_in, cudaStream_t stream) {
   prog.dbg_ops = g_stream_dbg_ops;
   prog.dbg_mode = g_stream_dbg_mode;
   prog.pf_steps = g_stream_pf_steps;
+  prog.poll_ns = g_stream_poll_ns;
   if (prog.w_slots <= 0 || prog.a_slots <= 0 || prog.w_slots + prog.a_slots > kStreamSlots) {
     prog.w_slots = g_stream_w_slots;
     prog.a_slots = g_stream_a_slots;
@@ -1003,6 +1005,12 @@ int bd_stream_set_debug(void* buf, int max_ops) {
 int bd_stream_set_ksplit(int ksplit) {  // before packing any weights: the packer and the program builder must agree
   BD_REQUIRE(ksplit == 1 || ksplit == 2 || ksplit == 4);
   stream_ksplit_small() = ksplit;
+  return BD_OK;
+}
+
+int bd_stream_set_poll_ns(int ns) {
+  BD_REQUIRE(ns >= 0 && ns <= 100000);
+  g_stream_poll_ns = ns;
   return BD_OK;
 }
 

@@ -91,6 +91,7 @@ struct StreamProgram {
   int dbg_mode;   // experiment switches (bd_stream_set_debug): bit0 no bias loads, bit1 no stores, bit2 32-byte stores
   int w_slots, a_slots;  // ring split, w_slots + a_slots <= kStreamSlots (0: defaults)
   int pf_steps;          // L2 prefetch distance of the weight stream, in ring steps (0: off)
+  int poll_ns;           // sleep between two polls of the grid barrier counter
   float sched[kStreamMaxIter][6];  // per iteration: t, dt, denom, var, 1-t, noise_scale   (sampling_x.py:62-68)
   StreamOp ops[kStreamMaxOps];
 };
@@ -188,10 +189,10 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 // Wait until every CTA has completed all ops before sequence number `seq` (counter >= G * seq). Bounded: a protocol bug
 // traps instead of hanging the box.
-__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
+__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target, unsigned int poll_ns = 32) {
   unsigned int spins = 0;
   while (ld_acquire_gpu(ctr) < target) {
-    __nanosleep(32);
+    __nanosleep(poll_ns);  // (tight polling is slower: 148-296 pollers hammer the line the arrivals have to update)
     if (++spins > (1u << 24)) {
       printf("bd_stream: grid barrier timeout block=%d thread=%d target=%u have=%u\n", blockIdx.x, threadIdx.x, target,
              ld_acquire_gpu(ctr));

@@ -280,6 +280,8 @@ int bd_stream_set_tuning(int w_slots, int a_slots, int mode);
 /* L2 prefetch distance of the weight stream in ring steps of ~28 KB per CTA (0 = off): the producer warp issues
  * cp.async.bulk.prefetch.L2 that far ahead of its shared-memory loads, so HBM keeps streaming while the ring is full. */
 int bd_stream_set_prefetch(int steps);
+/* sleep (ns) between two polls of the grid-barrier counter (default 32; tight polling is slower) */
+int bd_stream_set_poll_ns(int ns);
 /* k-split (1, 2 or 4; default 4) bd_stream_ksplit returns for small-N Linears. Set BEFORE packing weights. */
 int bd_stream_set_ksplit(int ksplit);
 /* k-split the engine uses for a Linear whose output goes through fp32 partials (N small next to the SM count) */

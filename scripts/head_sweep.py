@@ -32,23 +32,9 @@ def timed(reps=3):
     return e0.elapsed_time(e1) / reps
 
 
-for ks in (4, 2):
-    lib.bd_stream_set_ksplit(ks)
-    head = HeadRunner(sd, device=dev, tiled=False, **hc)
-    ref = None
-    for ws_, as_, pf in ((5, 2, 0), (4, 3, 0), (5, 2, 8)):
-        lib.bd_stream_set_tuning(ws_, as_, 0)
-        lib.bd_stream_set_prefetch(pf)
-        ms = timed()
-        torch.manual_seed(1)
-        x = head.sample(z, 7.5, S)
-        if ref is None:
-            ref = x.clone()
-        same = bool(torch.equal(x, ref))
-        print(f"ksplit {ks}  ring {ws_}+{as_}  prefetch {pf:3d} steps: {ms:7.2f} ms  {ms / (S + 1) * 1e3:7.1f} us/eval  "
-              f"{(S + 1) * 3.465e9 / (ms / 1e3) / 1e9:6.0f} GB/s   identical_output={same}", flush=True)
-    del head
-    torch.cuda.empty_cache()
-lib.bd_stream_set_ksplit(4)
-lib.bd_stream_set_prefetch(0)
-lib.bd_stream_set_tuning(5, 2, 0)
+head = HeadRunner(sd, device=dev, tiled=False, **hc)
+for ns in (8, 32, 64, 128, 256, 512):
+    lib.bd_stream_set_poll_ns(ns)
+    ms = timed()
+    print(f"barrier poll sleep {ns:4d} ns: {ms:7.2f} ms  {ms / (S + 1) * 1e3:7.1f} us/eval", flush=True)
+lib.bd_stream_set_poll_ns(32)
