@@ -16,6 +16,11 @@
 
 namespace bd {
 
+// byte offset of element (row, col) of a blocked bf16 activation (same rule as bd_stream.cuh::blk_off)
+__device__ __forceinline__ long long attn_blk_off(int row, int col) {
+  return (static_cast<long long>(col >> 6) << 14) + (row << 7) + ((((col >> 3) & 7) ^ (row & 7)) << 4) + ((col & 7) << 1);
+}
+
 struct AttnParams {
   const __nv_bfloat16* q;  // element (b, s, h, d) at q + b*q_sb + s*q_ss + h*q_sh + d
   long long q_sb, q_ss, q_sh;
@@ -30,6 +35,7 @@ struct AttnParams {
   int paged;
   __nv_bfloat16* out;  // (b, s, h, d) at out + b*o_sb + s*o_ss + h*o_sh + d
   long long o_sb, o_ss, o_sh;
+  int out_blocked;     // 1: out is the blocked [Hq*hd/64][128][64] swizzled image of rows b*Sq+s (operand of the stream engine)
   float* part_o;  // [splits][B][Hq][Sq][D] fp32 (unnormalised) when splits > 1
   float* part_ml; // [splits][B][Hq][Sq][2] (max, sum)
   int B, Sq, Sk, Hq, Hkv;
@@ -233,7 +239,11 @@ __global__ void __launch_bounds__(128) bd_attn_kernel(AttnParams p) {
 #pragma unroll
       for (int n = 0; n < HD / 8; ++n) {
         const uint32_t pk = pack_bf16(o_acc[n][2 * r] * inv, o_acc[n][2 * r + 1] * inv);
-        *reinterpret_cast<uint32_t*>(o + 8 * n + 2 * t) = pk;
+        if (p.out_blocked)
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out) +
+                                       attn_blk_off(b * p.Sq + qrow[r], h * HD + 8 * n + 2 * t)) = pk;
+        else
+          *reinterpret_cast<uint32_t*>(o + 8 * n + 2 * t) = pk;
       }
     }
   } else {
@@ -283,7 +293,13 @@ __global__ void __launch_bounds__(128) bd_attn_combine_kernel(AttnParams p) {
   const float inv = l > 0.f ? 1.0f / l : 0.f;
   __nv_bfloat16* o = p.out + b * p.o_sb + static_cast<long long>(s) * p.o_ss + h * p.o_sh;
 #pragma unroll
-  for (int i = 0; i < HD / 32; ++i) o[lane + 32 * i] = __float2bfloat16_rn(acc[i] * inv);
+  for (int i = 0; i < HD / 32; ++i) {
+    const __nv_bfloat16 v = __float2bfloat16_rn(acc[i] * inv);
+    if (p.out_blocked)
+      *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(p.out) + attn_blk_off(b * p.Sq + s, h * HD + lane + 32 * i)) = v;
+    else
+      o[lane + 32 * i] = v;
+  }
 }
 
 template <int HD>
@@ -329,8 +345,10 @@ size_t attn_llm_workspace_bytes(int R, int S, int Hq, int head_dim, int splits) 
 }
 int attn_run_llm(const __nv_bfloat16* q, const __nv_bfloat16* kpool, const __nv_bfloat16* vpool, const int* page_table,
                  int max_pages, const int* sk_dev, int sk_bound, __nv_bfloat16* out, int R, int S, int Hq, int Hkv,
-                 int head_dim, int causal, int splits, void* ws, size_t ws_bytes, bool pdl, cudaStream_t stream) {
+                 int head_dim, int causal, int splits, void* ws, size_t ws_bytes, bool pdl, cudaStream_t stream,
+                 int out_blocked) {
   AttnParams p{};
+  p.out_blocked = out_blocked;
   p.q = q;
   p.q_sb = static_cast<long long>(S) * Hq * head_dim;
   p.q_ss = static_cast<long long>(Hq) * head_dim;

@@ -12,13 +12,15 @@
 #include "bd_host.h"
 #include "bd_ptx.cuh"
 #include "bd_rowops.cuh"
+#include "bd_stream.cuh"
 
 namespace bd {
 
 struct AttnParams;
 int attn_run_llm(const __nv_bfloat16* q, const __nv_bfloat16* kpool, const __nv_bfloat16* vpool, const int* page_table,
                  int max_pages, const int* sk_dev, int sk_bound, __nv_bfloat16* out, int R, int S, int Hq, int Hkv,
-                 int head_dim, int causal, int splits, void* ws, size_t ws_bytes, bool pdl, cudaStream_t stream);
+                 int head_dim, int causal, int splits, void* ws, size_t ws_bytes, bool pdl, cudaStream_t stream,
+                 int out_blocked = 0);
 size_t attn_llm_workspace_bytes(int R, int S, int Hq, int head_dim, int splits);
 
 __device__ __forceinline__ float block_sum256(float v, float* red) {
@@ -181,6 +183,7 @@ static size_t al(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct LlmWs {
   size_t a, qkv, q, o, g, attn, gemm, total;
+  size_t s_a, s_o, s_g, s_part, s_sync;  // persistent path: blocked operands, fp32 k-split partials, barrier counter
 };
 
 static LlmWs llm_ws_layout(const bd_llm_weights_t& w, int M, int R, int S, int attn_splits) {
@@ -208,8 +211,100 @@ static LlmWs llm_ws_layout(const bd_llm_weights_t& w, int M, int R, int S, int a
   gw(2 * w.I, w.D);
   gw(w.D, w.I);
   L.gemm = take(gm);
+  if (w.stream_ctas > 0 && M <= 128) {
+    auto blk = [](size_t K) { return ((K + 63) / 64) * static_cast<size_t>(kSlotBytes); };
+    L.s_a = take(blk(w.D));
+    L.s_o = take(blk(static_cast<size_t>(w.Hq) * w.head_dim));
+    L.s_g = take(blk(w.I));
+    L.s_part = take(static_cast<size_t>(4) * 128 * w.D * 4);
+    L.s_sync = take(64);
+  }
   L.total = off;
   return L;
+}
+
+// One persistent launch: o_proj (+res) -> RMSNorm -> gate_up (SwiGLU) -> down (+res) -> next RMSNorm -> next layer's qkv
+// (or, after the last layer, the final norm). `first`: only the input RMSNorm + layer 0's qkv.
+static int llm_stream_segment(const bd_llm_weights_t& w, int li, bool first, void* hidden, int M, uint8_t* base,
+                              const LlmWs& L, __nv_bfloat16* qkv, int qkv_n, void* out, const float* out_add,
+                              int out_add_mod, cudaStream_t st) {
+  static thread_local StreamProgram prog;
+  prog = StreamProgram{};
+  prog.M = M;
+  prog.n_ctas = w.stream_ctas;
+  prog.n_iter = 1;
+  prog.cfg_mult = 1;
+  prog.sync = reinterpret_cast<unsigned int*>(base + L.s_sync);
+  const int D = w.D, G = w.stream_ctas, Ko = w.Hq * w.head_dim;
+  int n = 0;
+  auto gemm_op = [&](const void* W, const void* A, int N, int K, int ksplit, int epi, void* o, long long ld, bool blocked) {
+    StreamOp& op = prog.ops[n++];
+    op = StreamOp{};
+    op.kind = kOpGemm;
+    op.sub = epi;
+    op.N = N;
+    op.K = K;
+    op.ksplit = ksplit;
+    op.flags = blocked ? kFlagBlocked : 0;
+    op.wait_prev = 1;
+    op.p0 = W;
+    op.p1 = A;
+    op.o0 = o;
+    op.l0 = ld;
+  };
+  auto row = [&](int sub) -> StreamOp& {
+    StreamOp& op = prog.ops[n++];
+    op = StreamOp{};
+    op.kind = kOpRow;
+    op.sub = sub;
+    op.wait_prev = 1;
+    op.N = D;
+    op.f0 = w.eps;
+    op.o1 = hidden;
+    return op;
+  };
+  if (first) {
+    StreamOp& op = row(kRowLlmRms);
+    op.wait_prev = 0;
+    op.p1 = w.layers[0].ln1_w;
+    op.o0 = base + L.s_a;
+    gemm_op(w.layers[0].wqkv_s, base + L.s_a, qkv_n, D, 1, kEpiBias, qkv, qkv_n, false);
+  } else {
+    const bd_llm_layer_t& lw = w.layers[li];
+    const bool last = li + 1 == w.n_layers;
+    const int ks_o = stream_ksplit_for(D, Ko, G), ks_d = stream_ksplit_for(D, w.I, G);
+    gemm_op(lw.wo_s, base + L.s_o, D, Ko, ks_o, kEpiPartial, base + L.s_part, 0, false);
+    prog.ops[n - 1].wait_prev = 0;  // its operand comes from the attention kernel launched before this one
+    {
+      StreamOp& op = row(kRowLlmResRms);
+      op.p0 = base + L.s_part;
+      op.i0 = ks_o;
+      op.p1 = lw.ln2_w;
+      op.o0 = base + L.s_a;
+    }
+    gemm_op(lw.w_gate_up_s, base + L.s_a, 2 * w.I, D, 1, kEpiSwiglu8, base + L.s_g, 0, true);
+    gemm_op(lw.w_down_s, base + L.s_g, D, w.I, ks_d, kEpiPartial, base + L.s_part, 0, false);
+    {
+      StreamOp& op = row(kRowLlmResRms);
+      op.p0 = base + L.s_part;
+      op.i0 = ks_d;
+      if (last) {
+        op.p1 = w.final_norm_w;
+        op.i1 = 1;
+        op.o0 = out;
+        op.p3 = out_add;
+        op.i2 = out_add_mod > 0 ? out_add_mod : 1;
+      } else {
+        op.p1 = w.layers[li + 1].ln1_w;
+        op.o0 = base + L.s_a;
+      }
+    }
+    if (!last) gemm_op(w.layers[li + 1].wqkv_s, base + L.s_a, qkv_n, D, 1, kEpiBias, qkv, qkv_n, false);
+  }
+  prog.n_pre = 0;
+  prog.n_body = n;
+  prog.n_post = 0;
+  return stream_launch(prog, st);
 }
 
 }  // namespace bd
@@ -292,6 +387,36 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
     }
     return next_norm ? norm_to_bf16(next_norm) : BD_OK;
   };
+
+  // ---- AR block of one 128-row tile with stream-packed weights: the Linears / residual adds / norms of every layer run as
+  // persistent bd_stream_kernel segments; RoPE + KV append and the paged attention stay the kernels below ----
+  if (w.stream_ctas > 0 && stream_f32 && !causal && M <= 128 && w.stream_ctas == num_sms() && (qkv_n % 16) == 0 &&
+      D <= 6144 && (w.I % 64) == 0) {
+    // blocked operands are read in whole 128-row x 64-column tiles: padding rows / columns must be finite
+    BD_CUDA_TRY(cudaMemsetAsync(base + L.s_a, 0, L.s_sync - L.s_a, st));
+    BD_TRY(llm_stream_segment(w, 0, true, hidden, M, base, L, qkv, qkv_n, out, out_add, out_add_mod, st));
+    for (int li = 0; li < w.n_layers; ++li) {
+      const bd_llm_layer_t& lw = w.layers[li];
+      __nv_bfloat16* kpool = reinterpret_cast<__nv_bfloat16*>(kv_pool) + static_cast<long long>(li) * kv_layer_stride;
+      __nv_bfloat16* vpool = kpool + kv_v_offset;
+      const long long warps = static_cast<long long>(M) * (w.Hq + 2 * w.Hkv);
+      const unsigned grid = static_cast<unsigned>((warps * 32 + 255) / 256);
+      if (hd == 128)
+        BD_TRY(launch_k(qk_norm_rope_append_kernel<128, true>, dim3(grid), dim3(256), 0, st, false,
+                        (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
+                        (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq, w.Hkv, w.eps, M));
+      else
+        BD_TRY(launch_k(qk_norm_rope_append_kernel<64, true>, dim3(grid), dim3(256), 0, st, false,
+                        (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
+                        (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq, w.Hkv, w.eps, M));
+      BD_TRY(attn_run_llm(q, kpool, vpool, page_table, max_pages, seq_lens, sk_bound,
+                          reinterpret_cast<__nv_bfloat16*>(base + L.s_o), R, S, w.Hq, w.Hkv, hd, causal, attn_splits, aws,
+                          aws_bytes, pdl, st, /*out_blocked=*/1));
+      BD_TRY(llm_stream_segment(w, li, false, hidden, M, base, L, qkv, qkv_n, out, out_add, out_add_mod, st));
+    }
+    BD_TRY(launch_k(bump_seq_lens_kernel, dim3(1), dim3(256), 0, st, false, seq_lens, R, S));
+    return BD_OK;
+  }
 
   BD_TRY(norm_to_bf16(w.layers[0].ln1_w));
   for (int li = 0; li < w.n_layers; ++li) {

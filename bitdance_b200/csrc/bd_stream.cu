@@ -336,6 +336,75 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       }
       return;
     }
+    case kRowLlmRms:
+    case kRowLlmResRms: {
+      // Qwen3DecoderLayer on the fp32 residual stream of an AR block (transformers qwen3; oracle/llm.py stream_f32):
+      //   kRowLlmResRms: hidden += bf16(sum_s partial_s)   (the o_proj / down_proj output, rounded to bf16 by the Linear)
+      //   then  y = float(w) * (hidden * rstd)             (Qwen3RMSNorm in fp32)
+      //   i1 == 0: y -> bf16, blocked (operand of the next GEMM);  i1 == 1: the final norm: out fp32 = y + add[m % i2]
+      // p0 partials fp32 [S][M][D] (i0 = S), o1 hidden fp32 [M, D] in/out, p1 norm weight bf16 [D] (nullable for i1 == 0: no
+      // norm), p3 add table fp32 [i2][D] (nullable), o0 output
+      if (r >= M) return;
+      const int D = op.N, nvec = D / 8;
+      float* hid = reinterpret_cast<float*>(op.o1) + static_cast<long long>(r) * D;
+      float v[kRowVec][8];
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < kRowVec; ++i) {
+        const int c = tid + i * 128;
+        if (c < nvec) {
+          const float4 r0 = ldcg_f4(hid + c * 8), r1 = ldcg_f4(hid + c * 8 + 4);
+          const float res[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          if (op.sub == kRowLlmResRms) {
+            const float* part = reinterpret_cast<const float*>(op.p0);
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            for (int sp = 0; sp < op.i0; ++sp) {  // fixed order: deterministic
+              const float* q = part + (static_cast<long long>(sp) * M + r) * D + c * 8;
+              const float4 x0 = ldcg_f4(q), x1 = ldcg_f4(q + 4);
+              acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
+              acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] = res[j] + bf16_round(acc[j]);
+            *reinterpret_cast<float4*>(hid + c * 8) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+            *reinterpret_cast<float4*>(hid + c * 8 + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] = res[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+        }
+      }
+      if (!op.p1) return;
+      const float rstd = rsqrtf(epi_sum(ss, red, tid) / static_cast<float>(D) + op.f0);
+      const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(op.p1);
+#pragma unroll
+      for (int i = 0; i < kRowVec; ++i) {
+        const int c = tid + i * 128;
+        if (c < nvec) {
+          float wv[8], y[8];
+          bf16x8_to_f(*reinterpret_cast<const uint4*>(nw + c * 8), wv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = wv[j] * (v[i][j] * rstd);
+          if (op.i1) {
+            float* o = reinterpret_cast<float*>(op.o0) + static_cast<long long>(r) * D + c * 8;
+            if (op.p3) {
+              const float* add = reinterpret_cast<const float*>(op.p3) + static_cast<long long>(r % op.i2) * D + c * 8;
+              const float4 a0 = *reinterpret_cast<const float4*>(add), a1 = *reinterpret_cast<const float4*>(add + 4);
+              y[0] += a0.x; y[1] += a0.y; y[2] += a0.z; y[3] += a0.w; y[4] += a1.x; y[5] += a1.y; y[6] += a1.z; y[7] += a1.w;
+            }
+            *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          } else {
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(op.o0) + blk_off(r, c * 8)) = f_to_bf16x8(y);
+          }
+        }
+      }
+      return;
+    }
     default: return;
   }
 }

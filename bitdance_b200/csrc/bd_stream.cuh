@@ -49,6 +49,8 @@ enum : int {
   kRowSplitkLnMod = 5,// h += gate * (sum(partials) + bias); then kRowLnMod
   kRowFinal = 6,      // kRowSplitkLnMod without affine, then final Linear (+ 2 sigmoid - 1) -> pred
   kRowSde = 7,        // Euler–Maruyama / last Euler step on x; xb for the next evaluation
+  kRowLlmRms = 8,     // Qwen3 RMSNorm of an fp32 residual row -> blocked bf16
+  kRowLlmResRms = 9,  // residual += bf16(sum partials); then RMSNorm -> blocked bf16, or the final norm (+ pos table) -> fp32
 };
 
 // One op. Field meaning per kind:

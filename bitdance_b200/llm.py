@@ -6,6 +6,7 @@ the reference (modeling/t2i_pipeline.py:199-266). Accepts the HF state-dict key 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -17,12 +18,14 @@ PAGE = 64
 
 
 class LlmLayer(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln2_w", "q_norm_w", "k_norm_w", "wqkv", "wo", "w_gate_up", "w_down")]
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln2_w", "q_norm_w", "k_norm_w", "wqkv", "wo", "w_gate_up", "w_down",
+                                          "wqkv_s", "wo_s", "w_gate_up_s", "w_down_s")]
 
 
 class LlmWeights(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("D", "I", "n_layers", "Hq", "Hkv", "head_dim")] + [
-        ("eps", C.c_float), ("w_tiled", C.c_int), ("final_norm_w", C.c_void_p), ("layers", C.POINTER(LlmLayer))]
+        ("eps", C.c_float), ("w_tiled", C.c_int), ("stream_ctas", C.c_int), ("reserved_", C.c_int),
+        ("final_norm_w", C.c_void_p), ("layers", C.POINTER(LlmLayer))]
 
 
 def llm_config_dict(cfg) -> dict:
@@ -71,11 +74,19 @@ class KVCache:
 
 class LlmRunner:
     def __init__(self, state_dict: dict | None, cfg, device="cuda", prefix="model.", synthetic_seed: int | None = None,
-                 max_positions: int = 8192):
+                 max_positions: int = 8192, stream: bool | None = None):
+        """stream: also keep stream-major copies of the four Linears of every layer, so that AR blocks of one 128-row tile
+        run their GEMMs / residual adds / RMSNorms as persistent bd_stream_kernel segments (costs a second copy of the
+        decoder weights in HBM: 26 GB for Qwen3-14B)."""
         self.cfg = c = llm_config_dict(cfg)
         self.device = dev = torch.device(device)
         D, I, hd = c["hidden_size"], c["intermediate_size"], c["head_dim"]
         Hq, Hkv, L = c["num_attention_heads"], c["num_key_value_heads"], c["num_hidden_layers"]
+        qkv_n = (Hq + 2 * Hkv) * hd
+        if stream is None:  # default: off until opted in (BD_LLM_STREAM=1) — see DESIGN.md section 7
+            stream = os.environ.get("BD_LLM_STREAM", "0") == "1"
+        stream = bool(stream) and D % 64 == 0 and I % 64 == 0 and qkv_n % 16 == 0 and D <= 6144
+        n_ctas = ops.stream_num_ctas() if stream else 0
         self._keep = []
         layers = (LlmLayer * L)()
         gen = None
@@ -108,8 +119,18 @@ class LlmRunner:
                               get(p + "self_attn.k_proj.weight", (Hkv * hd, D)),
                               get(p + "self_attn.v_proj.weight", (Hkv * hd, D))], dim=0).contiguous()
             wo = get(p + "self_attn.o_proj.weight", (D, Hq * hd))
-            wgu, _ = ops.interleave16(get(p + "mlp.gate_proj.weight", (I, D)), get(p + "mlp.up_proj.weight", (I, D)))
+            gate, up = get(p + "mlp.gate_proj.weight", (I, D)), get(p + "mlp.up_proj.weight", (I, D))
+            wgu, _ = ops.interleave16(gate, up)
             wd = get(p + "mlp.down_proj.weight", (D, I))
+            if n_ctas:
+                # stream-major copies for the persistent engine (AR blocks of one 128-row tile)
+                sq = ops.stream_pack_weight(wqkv, None, n_ctas=n_ctas)
+                so = ops.stream_pack_weight(wo, None, ksplit=ops.stream_ksplit(D, Hq * hd, n_ctas), n_ctas=n_ctas)
+                sg = ops.stream_pack_weight(torch.cat([gate, up], dim=0), None, swiglu=True, n_ctas=n_ctas)
+                sdn = ops.stream_pack_weight(wd, None, ksplit=ops.stream_ksplit(D, I, n_ctas), n_ctas=n_ctas)
+                keep += [sq.data, so.data, sg.data, sdn.data]
+                lw.wqkv_s, lw.wo_s, lw.w_gate_up_s, lw.w_down_s = (t.data_ptr() for t in (sq, so, sg, sdn))
+            del gate, up
             wqkv, wo, wgu, wd = (ops.pack_weight(t).data for t in (wqkv, wo, wgu, wd))  # tile-major for HBM streaming
             keep += [ln1, ln2, qn, kn, wqkv, wo, wgu, wd]
             lw.ln1_w, lw.ln2_w, lw.q_norm_w, lw.k_norm_w = ln1.data_ptr(), ln2.data_ptr(), qn.data_ptr(), kn.data_ptr()
@@ -121,6 +142,7 @@ class LlmRunner:
         w.D, w.I, w.n_layers, w.Hq, w.Hkv, w.head_dim = D, I, L, Hq, Hkv, hd
         w.eps = c["rms_norm_eps"]
         w.w_tiled = 1
+        w.stream_ctas = n_ctas
         w.final_norm_w = fn.data_ptr()
         self._layers = layers
         w.layers = C.cast(layers, C.POINTER(LlmLayer))

@@ -191,12 +191,20 @@ typedef struct {
   const void* wo;                  /* bf16 [D, Hq * head_dim] */
   const void* w_gate_up;           /* bf16 [2 I, D]: bd_interleave16(gate_proj, up_proj) */
   const void* w_down;              /* bf16 [D, I] */
+  /* optional stream-major copies (bd_stream_pack_weight, n_ctas = stream_ctas) for AR blocks of one 128-row tile:
+   * wqkv_s [q|k|v] rows (ksplit 1), wo_s (ksplit bd_stream_ksplit(D, Hq*hd)), w_gate_up_s = cat(gate_proj, up_proj) with
+   * perm 1 (ksplit 1), w_down_s (ksplit bd_stream_ksplit(D, I)); NULL when stream_ctas == 0 */
+  const void *wqkv_s, *wo_s, *w_gate_up_s, *w_down_s;
 } bd_llm_layer_t;
 
 typedef struct {
   int D, I, n_layers, Hq, Hkv, head_dim;
   float eps;
   int w_tiled;                  /* 1: wqkv / wo / w_gate_up / w_down are in bd_pack_weight_tiles layout */
+  int stream_ctas;              /* > 0: the *_s weights exist, packed for this many CTAs: fp32-stream, non-causal passes with
+                                 * R*S <= 128 run every layer's four Linears, residual adds and RMSNorms as persistent
+                                 * bd_stream_kernel segments (RoPE / KV append / paged attention stay separate kernels) */
+  int reserved_;
   const void* final_norm_w;     /* bf16 [D] */
   const bd_llm_layer_t* layers; /* HOST array [n_layers] */
 } bd_llm_weights_t;
