@@ -451,17 +451,20 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
   gemm_op(w.cond_w, base + L.condb, w.cond_b, D, w.Dz, 1, kEpiBias, kActNone, base + L.cemb, D, false);
   gemm_op(w.time2_w, base + L.th, w.time2_b, D, D, 1, kEpiBias, kActNone, base + L.temb, D, false);
   prog.ops[n - 1].i1 = S + 1;
-  prog.n_pre = n;
-  // ---- one evaluation + SDE step ----
-  gemm_op(w.input_proj_w, base + L.xb, w.input_proj_b, D, C, 1, kEpiBias, kActNone, base + L.h, D, false);
-  {
+  {  // y of evaluation 0 (the y of evaluation i+1 is produced by evaluation i's SDE op)
     StreamOp& op = row_op_(kRowSiluAdd);
     op.p0 = base + L.temb;
     op.p1 = base + L.cemb;
     op.o0 = base + L.y;
     op.N = D;
   }
+  prog.n_pre = n;
+  // ---- one evaluation + SDE step ----
+  // input_proj (needs xb) and the adaLN GEMM (needs y) both depend only on the previous SDE op: the second one skips the
+  // barrier of the first (wait_prev = -1), so the two weight streams run back to back
+  gemm_op(w.input_proj_w, base + L.xb, w.input_proj_b, D, C, 1, kEpiBias, kActNone, base + L.h, D, false);
   gemm_op(w.ada_w, base + L.y, w.ada_b, n_mod, D, 1, kEpiBias, kActNone, mod, n_mod, false);
+  prog.ops[n - 1].wait_prev = -1;
   {
     StreamOp& op = row_op_(kRowLnMod);
     op.p0 = base + L.h;
@@ -550,6 +553,10 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
     op.o1 = base + L.xb;
     op.o2 = x_out;
     op.N = C;
+    op.p4 = base + L.temb;  // + y of the next evaluation
+    op.p5 = base + L.cemb;
+    op.o3 = base + L.y;
+    op.i0 = D;
   }
   prog.n_body = n - prog.n_pre;
   prog.n_post = 0;

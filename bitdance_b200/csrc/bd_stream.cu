@@ -302,37 +302,54 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       return;
     }
     case kRowSde: {  // sampling_x.py:24-41 with explicit round-to-nearest ops (torch rounds every op separately)
-      if (r >= prog.rows_x || tid >= op.N) return;
-      const int C = op.N, nx = prog.rows_x;
-      const float* pred = reinterpret_cast<const float*>(op.p0);
-      float* x = reinterpret_cast<float*>(op.o0);
-      const long long i = static_cast<long long>(r) * C + tid;
-      const long long n = static_cast<long long>(nx) * C;
-      const float t = prog.sched[it][0], dt = prog.sched[it][1], denom = prog.sched[it][2], var = prog.sched[it][3],
-                  omt = prog.sched[it][4], nscale = prog.sched[it][5];
-      const bool last = (it == prog.n_iter - 1);
-      const float xv = x[i];
-      float v = __fdiv_rn(__fsub_rn(__ldcg(pred + i), xv), denom);
-      if (prog.cfg_mult == 2) {
-        const float vu = __fdiv_rn(__fsub_rn(__ldcg(pred + n + i), xv), denom);
-        v = __fadd_rn(vu, __fmul_rn(prog.cfg, __fsub_rn(v, vu)));
+      // + (p4 != null) y of the NEXT evaluation, y = silu(temb[it + 1] + cemb[r]) -> o3 blocked: it depends on nothing the
+      //   sampler computes, and doing it here removes one op (and one grid barrier) from every evaluation
+      if (r < prog.rows_x && tid < op.N) {
+        const int C = op.N, nx = prog.rows_x;
+        const float* pred = reinterpret_cast<const float*>(op.p0);
+        float* x = reinterpret_cast<float*>(op.o0);
+        const long long i = static_cast<long long>(r) * C + tid;
+        const long long n = static_cast<long long>(nx) * C;
+        const float t = prog.sched[it][0], dt = prog.sched[it][1], denom = prog.sched[it][2], var = prog.sched[it][3],
+                    omt = prog.sched[it][4], nscale = prog.sched[it][5];
+        const bool last = (it == prog.n_iter - 1);
+        const float xv = x[i];
+        float v = __fdiv_rn(__fsub_rn(__ldcg(pred + i), xv), denom);
+        if (prog.cfg_mult == 2) {
+          const float vu = __fdiv_rn(__fsub_rn(__ldcg(pred + n + i), xv), denom);
+          v = __fadd_rn(vu, __fmul_rn(prog.cfg, __fsub_rn(v, vu)));
+        }
+        float xn;
+        if (last) {
+          xn = __fadd_rn(xv, __fmul_rn(v, dt));
+        } else {
+          const float nz = reinterpret_cast<const float*>(op.p1)[static_cast<long long>(it + 1) * n + i];
+          const float score = __fdiv_rn(__fsub_rn(__fmul_rn(t, v), xv), var);
+          const float drift = __fadd_rn(v, __fmul_rn(omt, score));
+          xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(drift, dt)), __fmul_rn(nscale, nz));
+        }
+        x[i] = xn;
+        if (last) {
+          reinterpret_cast<float*>(op.o2)[i] = xn;
+        } else {
+          const __nv_bfloat16 b = __float2bfloat16_rn(xn);
+          uint8_t* xb = reinterpret_cast<uint8_t*>(op.o1);
+          for (int g = 0; g < prog.cfg_mult; ++g) *reinterpret_cast<__nv_bfloat16*>(xb + blk_off(g * nx + r, tid)) = b;
+        }
       }
-      float xn;
-      if (last) {
-        xn = __fadd_rn(xv, __fmul_rn(v, dt));
-      } else {
-        const float nz = reinterpret_cast<const float*>(op.p1)[static_cast<long long>(it + 1) * n + i];
-        const float score = __fdiv_rn(__fsub_rn(__fmul_rn(t, v), xv), var);
-        const float drift = __fadd_rn(v, __fmul_rn(omt, score));
-        xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(drift, dt)), __fmul_rn(nscale, nz));
-      }
-      x[i] = xn;
-      if (last) {
-        reinterpret_cast<float*>(op.o2)[i] = xn;
-      } else {
-        const __nv_bfloat16 b = __float2bfloat16_rn(xn);
-        uint8_t* xb = reinterpret_cast<uint8_t*>(op.o1);
-        for (int g = 0; g < prog.cfg_mult; ++g) *reinterpret_cast<__nv_bfloat16*>(xb + blk_off(g * nx + r, tid)) = b;
+      if (op.p4 && r < M && it + 1 < prog.n_iter) {
+        const int D = op.i0;
+        const __nv_bfloat16* te = reinterpret_cast<const __nv_bfloat16*>(op.p4) + static_cast<long long>(it + 1) * D;
+        const __nv_bfloat16* ce = reinterpret_cast<const __nv_bfloat16*>(op.p5) + static_cast<long long>(r) * D;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(op.o3);
+        for (int c = tid; c < D / 8; c += 128) {
+          float a[8], b[8], o[8];
+          bf16x8_to_f(ldcg_u4(te + c * 8), a);
+          bf16x8_to_f(ldcg_u4(ce + c * 8), b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = siluf_(bf16_round(a[j] + b[j]));
+          *reinterpret_cast<uint4*>(dst + blk_off(r, c * 8)) = f_to_bf16x8(o);
+        }
       }
       return;
     }

@@ -75,6 +75,7 @@ struct StreamOp {
   void* o0;
   void* o1;
   void* o2;
+  void* o3;
   long long l0, l1;
   float f0;
   int i0, i1, i2;

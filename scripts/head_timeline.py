@@ -42,18 +42,18 @@ for path in (["stream", "tiled"] if head.w is not None else ["stream"]):
           f"{(S + 1) * 3.465e9 / (ms / 1e3) / 1e9:.0f} GB/s of the head's weight bytes")
 
 G = ops.stream_num_ctas()
-nops = 6 + 47 * 2
+nops = 7 + 46 * 2
 dbg = torch.zeros(nops * G * 8, dtype=torch.int64, device=dev)
 lib.bd_stream_set_debug(C.c_void_p(dbg.data_ptr()), nops)
 head.sample(z, 7.5, S, path="stream")
 torch.cuda.synchronize()
 lib.bd_stream_set_debug(None, 0)
 d = dbg.view(nops, G, 8).cpu().double() / 1e3
-names = ["cast", "tfreq", "init", "time0", "cond", "time2"]
-body = ["input_proj", "silu_add", "ada", "ln0"]
+names = ["cast", "tfreq", "init", "time0", "cond", "time2", "silu_add0"]
+body = ["input_proj", "ada", "ln0"]
 for b in range(6):
     body += [f"b{b}.wqkv", f"b{b}.attn", f"b{b}.wo", f"b{b}.row_wo", f"b{b}.w1", f"b{b}.w2", f"b{b}.row_w2"]
-body += ["sde"]
+body += ["sde+silu"]
 names = names + body + body
 t_prev = None
 print("op                 done(us)  dur(us) | arrive spread (med->max)")
@@ -66,7 +66,7 @@ for q in range(nops):
         t_prev = d[q, :, 4][d[q, :, 4] > 0].min().item()
         t0 = t_prev
     dur = done - t_prev
-    if q >= 6 + 47:
+    if q >= 7 + 46:
         key = names[q].split(".")[-1]
         tot[key] = tot.get(key, 0.0) + dur
         print(f"{names[q]:16s} {done - t0:9.1f} {dur:8.1f} | {done - v.median().item():6.1f}")
