@@ -76,3 +76,36 @@ def test_head_sampler_deterministic_and_seeded_noise():
     torch.manual_seed(7)
     nz = runner.draw_noise(1, 16, 3)
     assert torch.equal(nz[0], n0) and torch.equal(nz[1], n1)
+
+
+def test_head_full_size_properties():
+    """BASELINE size (BitDance-14B-64x head: D=5120, 6 blocks, 1.76 B parameters; R=2, pn=64, S=50): too big for the CPU
+    oracle, so size-independent properties — the persistent kernel is run-to-run bit-identical, its output does not depend
+    on the engine's ring split, and it agrees with the multi-kernel path (same arithmetic, different accumulation order:
+    the chaotic 51-step sampler amplifies bf16 ulps, so agreement is on signs)."""
+    from bitdance_b200 import _lib
+    from bitdance_b200.head import HeadRunner, head_spec
+    from bitdance_b200.synthetic import MODELS, _gpu_state_dict
+    hc = MODELS["BitDance-14B-64x"]["head"]
+    dev = torch.device("cuda")
+    sd = _gpu_state_dict(head_spec(hc["ch_target"], hc["ch_cond"], hc["ch_latent"], hc["depth_latent"], hc["depth_adanln"],
+                                   hc["use_swiglu"]), 2, dev)
+    head = HeadRunner(sd, device=dev, **hc)
+    del sd
+    lib = _lib.load()
+    R, pn, S = 2, 64, 50
+    torch.manual_seed(0)
+    z = torch.randn(R, pn, hc["ch_cond"], device=dev)
+    noise = head.draw_noise(1, pn, S)
+    a = head.sample(z, 7.5, S, noise=noise, path="stream")
+    b = head.sample(z, 7.5, S, noise=noise, path="stream")
+    assert torch.equal(a, b), "persistent kernel not deterministic"
+    assert torch.isfinite(a).all() and a.abs().max().item() < 50.0
+    lib.bd_stream_set_tuning(4, 3, 0)
+    c = head.sample(z, 7.5, S, noise=noise, path="stream")
+    lib.bd_stream_set_tuning(5, 2, 0)
+    assert torch.equal(a, c), "result depends on the ring split"
+    t = head.sample(z, 7.5, S, noise=noise, path="tiled")
+    agree = (torch.sign(a) == torch.sign(t)).float().mean().item()
+    print(f"14B-64x head, stream vs multi-kernel path: sign agreement {agree:.4f}, mean |diff| {(a - t).abs().mean().item():.4f}")
+    assert agree > 0.9
