@@ -81,8 +81,7 @@ def test_head_sampler_deterministic_and_seeded_noise():
 def test_head_full_size_properties():
     """BASELINE size (BitDance-14B-64x head: D=5120, 6 blocks, 1.76 B parameters; R=2, pn=64, S=50): too big for the CPU
     oracle, so size-independent properties — the persistent kernel is run-to-run bit-identical, its output does not depend
-    on the engine's ring split, and it agrees with the multi-kernel path (same arithmetic, different accumulation order:
-    the chaotic 51-step sampler amplifies bf16 ulps, so agreement is on signs)."""
+    on the engine's ring split, and it agrees with the multi-kernel path where agreement is meaningful (see below)."""
     from bitdance_b200 import _lib
     from bitdance_b200.head import HeadRunner, head_spec
     from bitdance_b200.synthetic import MODELS, _gpu_state_dict
@@ -91,7 +90,6 @@ def test_head_full_size_properties():
     sd = _gpu_state_dict(head_spec(hc["ch_target"], hc["ch_cond"], hc["ch_latent"], hc["depth_latent"], hc["depth_adanln"],
                                    hc["use_swiglu"]), 2, dev)
     head = HeadRunner(sd, device=dev, **hc)
-    del sd
     lib = _lib.load()
     R, pn, S = 2, 64, 50
     torch.manual_seed(0)
@@ -105,7 +103,32 @@ def test_head_full_size_properties():
     c = head.sample(z, 7.5, S, noise=noise, path="stream")
     lib.bd_stream_set_tuning(5, 2, 0)
     assert torch.equal(a, c), "result depends on the ring split"
-    t = head.sample(z, 7.5, S, noise=noise, path="tiled")
-    agree = (torch.sign(a) == torch.sign(t)).float().mean().item()
-    print(f"14B-64x head, stream vs multi-kernel path: sign agreement {agree:.4f}, mean |diff| {(a - t).abs().mean().item():.4f}")
-    assert agree > 0.9
+    # BASELINE-size parity against the CPU oracle (bf16 rounding policy) on the FIRST evaluation, where every implementation
+    # sees identical inputs (x = cat[noise0, noise0], t = 0): one oracle evaluation of the 1.76 B-parameter head takes
+    # ~10-20 s on the host cores. Both GPU paths are checked; after that the sampler is chaotic with random-init weights
+    # (CFG 7.5 multiplies every difference), so later evaluations are only compared teacher-forced on small models above.
+    from oracle import head as oh
+    xs, ts = head.sample(z, 7.5, S, noise=noise, path="stream", trace=True)
+    xt, tt = head.sample(z, 7.5, S, noise=noise, path="tiled", trace=True)
+    assert torch.equal(xs, a)
+    sd_cpu = {k: v.float().cpu() for k, v in sd.items()}
+    x0 = torch.cat([noise[0], noise[0]], dim=0).cpu()
+    with torch.no_grad():
+        ref = oh.head_forward(sd_cpu, x0, torch.zeros(R), z.cpu(), rnd=oh.bf16).reshape(R * pn, -1)
+    del sd_cpu
+    for name, tr in (("stream", ts), ("tiled", tt)):
+        d0 = (tr[0].cpu() - ref).abs()
+        print(f"14B-64x head [{name}] vs oracle, first evaluation: |diff| max {d0.max().item():.4f} mean {d0.mean().item():.5f} "
+              f"(outputs in (-1, 1), |ref| mean {ref.abs().mean().item():.3f})")
+        # 4096 outputs of a 6-block, D = 5120 bf16 network: mean at the bf16 rounding level, max a few tens of ulps
+        assert d0.mean().item() < 2e-2 and d0.max().item() < 0.25, name
+    dst = (ts[0] - tt[0]).abs()
+    print(f"  stream vs tiled: max {dst.max().item():.4f} mean {dst.mean().item():.5f}")
+    S2 = 3
+    noise2 = head.draw_noise(2, pn, S2)
+    a2 = head.sample(z, 1.0, S2, noise=noise2, path="stream")
+    t2 = head.sample(z, 1.0, S2, noise=noise2, path="tiled")
+    agree = (torch.sign(a2) == torch.sign(t2)).float().mean().item()
+    # reported, loosely bounded: with random-init weights the x-prediction is ~0, so the signs of the sample hang on rounding
+    print(f"  3 steps without guidance: sign agreement {agree:.4f}, mean |diff| {(a2 - t2).abs().mean().item():.5f}")
+    assert agree > 0.6
