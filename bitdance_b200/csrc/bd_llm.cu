@@ -390,7 +390,8 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
 
   // ---- AR block of one 128-row tile with stream-packed weights: the Linears / residual adds / norms of every layer run as
   // persistent bd_stream_kernel segments; RoPE + KV append and the paged attention stay the kernels below ----
-  if (w.stream_ctas > 0 && stream_f32 && !causal && M <= 128 && w.stream_ctas == num_sms() && (qkv_n % 16) == 0 &&
+  if (w.stream_ctas > 0 && stream_f32 && !causal && M <= 128 && w.stream_ctas == num_sms() && w.stream_ctas >= M &&
+      (qkv_n % 16) == 0 &&
       D <= 6144 && (w.I % 64) == 0) {
     // blocked operands are read in whole 128-row x 64-column tiles: padding rows / columns must be finite
     BD_CUDA_TRY(cudaMemsetAsync(base + L.s_a, 0, L.s_sync - L.s_a, st));

@@ -255,3 +255,33 @@ def test_imagenet_sample_vs_reference():
         assert torch.equal(fc, model.freqs_cis) and torch.equal(mask, model.attn_mask[0, 0])
     finally:
         torch._dynamo.config.disable = old_disable
+
+
+def test_vt_forward_host_logic_vs_reference(ref):
+    """the image-list bucketing / flattening of ``VQModel.vt_forward`` and
+    ``vt_forward_maxpad`` (autoencoder.py:402-511) is host logic re-expressed in the API mirror; both versions are driven
+    with the same stand-in ``encode`` (the convolutional encoder is pinned separately) and must agree exactly."""
+    import types
+    import torch.nn.functional as F
+    from bitdance_b200.modeling.vision_encoder.autoencoder import VQModel as Mine
+
+    def fake_encode(x, f=16, C=8):
+        p = F.avg_pool2d(x, f)                                    # [B, 3, H/f, W/f]
+        feats = torch.cat([p * (k + 1) for k in range(C // 3 + 1)], dim=1)[:, :C]
+        return torch.where(torch.sin(37.0 * feats) > 0, 1.0, -1.0)
+
+    torch.manual_seed(0)
+    sizes = [(64, 64), (96, 64), (64, 64), (128, 96), (96, 64), (64, 64), (64, 64)]
+    imgs = [torch.randn(1, 3, h, w) for h, w in sizes]
+    stub = types.SimpleNamespace(encode=lambda x: fake_encode(x))
+    for ps in (1, 2):
+        a = ref.ae.VQModel.vt_forward(stub, imgs, max_bs=2, ps=ps)
+        b = Mine.vt_forward(stub, imgs, max_bs=2, ps=ps)
+        assert a.shape == b.shape and torch.equal(a, b)
+    # maxpad: stride 32 with a stride-32 stand-in encoder; includes a "long" image and every normal bucket boundary
+    sizes2 = [(384, 256), (416, 384), (1024, 512), (512, 512), (1056, 320), (768, 800), (96, 1536)]
+    imgs2 = [torch.randn(1, 3, h, w) for h, w in sizes2]
+    stub2 = types.SimpleNamespace(encode=lambda x: fake_encode(x, f=32))
+    a = ref.ae.VQModel.vt_forward_maxpad(stub2, imgs2, max_bs=2)
+    b = Mine.vt_forward_maxpad(stub2, imgs2, max_bs=2)
+    assert a.shape == b.shape and torch.equal(a, b)
