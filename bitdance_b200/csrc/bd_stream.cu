@@ -1121,6 +1121,21 @@ size_t bd_stream_packed_elems(int N, int K) {
 
 int bd_stream_ksplit(int N, int K, int n_ctas) { return stream_ksplit_for(N, K, n_ctas); }
 
+// tests: the work split of CTA c for a GEMM op. out[0..5] = split, unit0, units, kb0, kbs, npass; then per pass i
+// (up to 8): out[6 + 3 i ..] = first unit (relative to unit0), width in rows, offset of the pass's first slot in 2 KB units.
+int bd_stream_partition_info(int N, int K, int ksplit, int n_ctas, int c, long long* out, int cap) {
+  BD_REQUIRE(out && cap >= 6 && N > 0 && (N % 16) == 0 && K > 0 && ksplit >= 1 && n_ctas >= ksplit && c >= 0 && c < n_ctas);
+  BD_REQUIRE(((K + 63) / 64) % ksplit == 0);
+  const StreamPart p = stream_partition(N, K, ksplit, n_ctas, c);
+  out[0] = p.split; out[1] = p.unit0; out[2] = p.units; out[3] = p.kb0; out[4] = p.kbs; out[5] = p.npass;
+  for (int i = 0; i < p.npass && 6 + 3 * i + 2 < cap; ++i) {
+    out[6 + 3 * i] = stream_pass_u0(p, i);
+    out[6 + 3 * i + 1] = (stream_pass_u0(p, i + 1) - stream_pass_u0(p, i)) * 16;
+    out[6 + 3 * i + 2] = stream_pass_offset(N, p, i);
+  }
+  return BD_OK;
+}
+
 int bd_stream_pack_weight(const void* W, int64_t ldw, int N, int K, int ksplit, int n_ctas, int perm, int hidden,
                           const void* bias, void* out, void* bias_out, bd_stream_t stream) {
   BD_REQUIRE(W && out && N > 0 && K > 0 && (N % 16) == 0 && ldw >= K && n_ctas > 0 && ksplit >= 1);

@@ -295,6 +295,10 @@ int bd_stream_set_ksplit(int ksplit);
 /* k-split the engine uses for a Linear whose output goes through fp32 partials (N small next to the SM count) */
 int bd_stream_ksplit(int N, int K, int n_ctas);
 size_t bd_stream_packed_elems(int N, int K); /* bf16 elements of a stream-packed [N, K] weight (K padded to 64) */
+/* tests: CTA c's share of a GEMM op: out[0..5] = k-split index, first 16-row unit, units, first k-block, k-blocks, passes;
+ * then per pass (first unit relative to unit0, width in rows <= 128, offset of its first slot in the packed weight in
+ * 2 KB units). Host arithmetic only (the same inline functions the kernel and the packer use). */
+int bd_stream_partition_info(int N, int K, int ksplit, int n_ctas, int c, long long* out, int cap);
 /* W [N, K] row-major bf16 (ldw) -> stream-major: the weight bytes CTA c needs are one contiguous range, already in the
  * 128B-swizzled K-major shared-memory image. perm 0: rows as they are; perm 1 (SwiGLU, N = 2*hidden): packed unit u =
  * [rows 8u..8u+7 of W[:hidden] | rows 8u..8u+7 of W[hidden:]]. bias (nullable) -> bias_out [N] in packed row order. */

@@ -121,3 +121,46 @@ def test_stream_host_policy_cpu():
     assert lib.bd_stream_ksplit(15360, 5120, 148) == 1                # wqkv / w1: enough units
     assert lib.bd_stream_ksplit(256, 256, 148) == 1                   # tiny models: too few k-blocks to split
     assert lib.bd_stream_set_tuning(5, 2, 0) == 0 and lib.bd_stream_set_tuning(6, 2, 0) != 0   # 7 ring slots in total
+
+
+def test_stream_partition_covers_every_weight_byte_once_cpu():
+    """The work split the kernel, the packer and the host share (csrc/bd_stream.cuh::stream_partition): for every GEMM
+    shape on the path — and the ImageNet / tiny-model shapes — the (k-split, 16-row unit) space is dealt to the CTAs
+    exactly once, passes are <= 128 rows, and the per-pass slot offsets tile the packed weight without gaps or overlap."""
+    import ctypes as C
+    import __graft_entry__ as ge
+    ge.build()
+    from bitdance_b200 import _lib
+    lib = _lib.load()
+    shapes = [(15360, 5120), (5120, 5120), (5120, 7680), (71680, 5120), (5120, 32), (5120, 256), (7168, 5120),
+              (34816, 5120), (5120, 17408), (3584, 256), (768, 256), (256, 384), (160, 64), (1536, 256), (2304, 768),
+              (4096, 1024), (3840, 1280), (16, 64), (2368, 64)]
+    for G in (148, 132, 8):
+        for N, K in shapes:
+            KB = (K + 63) // 64
+            for S in (1, 2, 4):
+                if KB % S or G < S:
+                    continue
+                U = N // 16
+                seen = [[0] * U for _ in range(S)]
+                spans = []
+                out = (C.c_longlong * 2048)()
+                for c in range(G):
+                    assert lib.bd_stream_partition_info(N, K, S, G, c, out, 2048) == 0
+                    split, unit0, units, kb0, kbs, npass = (int(out[i]) for i in range(6))
+                    assert kbs == KB // S and (units == 0 or kb0 == split * kbs)
+                    assert npass == (units + 7) // 8
+                    covered = 0
+                    for i in range(npass):
+                        u0, width, off = int(out[6 + 3 * i]), int(out[7 + 3 * i]), int(out[8 + 3 * i])
+                        assert 16 <= width <= 128 and width % 16 == 0 and u0 == covered
+                        assert off == (split * U + unit0 + u0) * kbs
+                        spans.append((off, off + (width // 16) * kbs))
+                        covered += width // 16
+                    assert covered == units
+                    for u in range(unit0, unit0 + units):
+                        seen[split][u] += 1
+                assert all(v == 1 for row in seen for v in row), (N, K, S, G)
+                spans.sort()
+                assert spans[0][0] == 0 and spans[-1][1] == S * U * (KB // S)
+                assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])), (N, K, S, G)
