@@ -34,10 +34,14 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, int splits, float* partial,
                        const GemmEpi& epi, bool pdl, cudaStream_t stream, int w_tiled) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    BD_CUDA_TRY(cudaFuncSetAttribute(bd_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+  {  // per device, not per process
+    static bool attr_set[64] = {};
+    int dev = 0;
+    BD_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      BD_CUDA_TRY(cudaFuncSetAttribute(bd_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + BN - 1) / BN, splits);
   LaunchCfg lc(grid, dim3(kGemmThreads), Cfg::kSmemBytes, stream, pdl);

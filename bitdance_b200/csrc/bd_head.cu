@@ -334,9 +334,16 @@ static HeadWs head_ws_layout(const bd_head_weights_t& w, int M, int n_rows_x, in
 // ---------------------------------------------------------------------------------------------------------------------
 struct HeadStreamWs {
   size_t xb, h, y, mod, a, qkv, o, g, cemb, condb, tfreq, th, temb, part, pred, x, sync, total;
+  size_t mod_bytes, y_bytes;  // one modulation buffer / one y image (fillers: 2 mod buffers, S + 1 y images)
 };
 
 static size_t blocked_bytes(int K) { return static_cast<size_t>((K + 63) / 64) * kSlotBytes; }
+
+// Filler policy (bd_head_set_fillers): 0 = the adaLN GEMM runs in line at the start of every evaluation (round-1 program);
+// 1 = the adaLN GEMM of evaluation i + 1 runs as filler pieces in the bubbles of evaluation i (bd_stream.cuh, FILLERS).
+static int g_head_fillers = 1;
+static int g_head_fill_row_kb = 22;   // k-blocks (of 128 weight rows x 64) wanted in a slot that hides a row op
+static int g_head_fill_gemm_kb = 8;   // ... in a slot that hides a GEMM -> GEMM boundary
 
 static HeadStreamWs head_stream_ws_layout(const bd_head_weights_t& w, int S) {
   HeadStreamWs L{};
@@ -348,10 +355,12 @@ static HeadStreamWs head_stream_ws_layout(const bd_head_weights_t& w, int S) {
   };
   const size_t D = w.D;
   const size_t n_mod = static_cast<size_t>(w.n_ada) * 6 * D + 2 * D;
+  L.mod_bytes = (128 * n_mod * 2 + 1023) & ~size_t(1023);
+  L.y_bytes = blocked_bytes(w.D);
   L.xb = take(blocked_bytes(w.C));
   L.h = take(128 * D * 2);
-  L.y = take(blocked_bytes(w.D));
-  L.mod = take(128 * n_mod * 2);
+  L.y = take(L.y_bytes * static_cast<size_t>(S + 1));
+  L.mod = take(2 * L.mod_bytes);
   L.a = take(blocked_bytes(w.D));
   L.qkv = take(blocked_bytes(3 * w.D));  // blocked: the attention op fetches its Q / K / V tiles by bulk copy
   L.o = take(blocked_bytes(w.D));
@@ -369,6 +378,40 @@ static HeadStreamWs head_stream_ws_layout(const bd_head_weights_t& w, int S) {
   return L;
 }
 
+// Cut the adaLN GEMM (P passes per CTA x KB k-blocks) into pieces for `n_slots` bubbles whose wanted sizes are `want`
+// (k-blocks). Sizes are scaled so that the pieces add up to the whole GEMM; a piece never spans two passes; sizes are
+// multiples of the ring step. out[slot] = list of (pass, kb0, kbn).
+struct HeadPiece { int slot, pass, kb0, kbn; };
+static int plan_head_pieces(int P, int KB, const int* want, int n_slots, HeadPiece* out, int cap) {
+  long long total_want = 0;
+  for (int i = 0; i < n_slots; ++i) total_want += want[i];
+  const long long supply = static_cast<long long>(P) * KB;
+  if (total_want <= 0 || supply <= 0) return 0;
+  int n = 0, pass = 0, kb = 0;
+  long long given = 0, wanted = 0;
+  for (int sl = 0; sl < n_slots && pass < P; ++sl) {
+    wanted += want[sl];
+    // cumulative target keeps rounding errors from piling up; the last slot takes whatever is left
+    long long target = sl == n_slots - 1 ? supply : (wanted * supply + total_want / 2) / total_want;
+    long long d = target - given;
+    d = (d + kKbPerStep - 1) / kKbPerStep * kKbPerStep;
+    while (d > 0 && pass < P) {
+      int take = static_cast<int>(d < KB - kb ? d : KB - kb);
+      if (KB - kb - take < 2 * kKbPerStep) take = KB - kb;  // no crumbs at the end of a pass
+      if (n >= cap) return -1;
+      out[n++] = HeadPiece{sl, pass, kb, take};
+      given += take;
+      d -= take;
+      kb += take;
+      if (kb >= KB) {
+        kb = 0;
+        ++pass;
+      }
+    }
+  }
+  return (pass >= P) ? n : -1;
+}
+
 static int head_sample_stream(const bd_head_weights_t& w, const float* cond, const float* noise, const float* sched_host,
                               int B, int pn, int cfg_mult, float cfg, int S, float* x_out, float* trace, void* workspace,
                               size_t workspace_bytes, cudaStream_t st) {
@@ -377,13 +420,37 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
   BD_REQUIRE(M <= 128 && S + 1 <= kStreamMaxIter && S + 1 <= 128 && G > 0 && G == num_sms());
   BD_REQUIRE(G >= M && G >= S + 1);  // row ops: token row r (timestep row r) is handled by CTA r
   BD_REQUIRE((D % 64) == 0 && (w.Dz % 8) == 0 && C <= 64 && (w.hidden % 8) == 0 && D <= 6144);
-  BD_REQUIRE(4 + 7 * w.n_blocks + 1 + 6 <= kStreamMaxOps);
   const int n_mod = w.n_ada * 6 * D + 2 * D;
   const HeadStreamWs L = head_stream_ws_layout(w, S);
   if (workspace_bytes < L.total) return BD_ERR_WORKSPACE;
   uint8_t* base = static_cast<uint8_t*>(workspace);
   // blocked operands are read in whole 64-column k-blocks and 128-row tiles: padding must be finite (zero)
   BD_CUDA_TRY(cudaMemsetAsync(base, 0, L.total, st));
+
+  // ---- filler plan: slots in GEMM order = after ln0, and per block after wo (row op), after w1 (boundary), after w2
+  // (row op; not for the last block, whose final-row op uses the A ring as scratch) ----
+  constexpr int kMaxPieces = 64;
+  HeadPiece pieces[kMaxPieces];
+  int n_pieces = 0;
+  const int n_slots = 3 * w.n_blocks;  // 1 + 3 * n_blocks - 1
+  bool fill = g_head_fillers != 0 && S >= 1;
+  if (fill) {
+    int P = 0;
+    for (int c = 0; c < G; ++c) {
+      const StreamPart p = stream_partition(n_mod, D, 1, G, c);
+      P = p.npass > P ? p.npass : P;
+    }
+    int want[3 * BD_HEAD_MAX_BLOCKS];
+    want[0] = g_head_fill_row_kb;
+    for (int b = 0; b < w.n_blocks; ++b) {
+      want[1 + 3 * b] = g_head_fill_row_kb;
+      want[2 + 3 * b] = g_head_fill_gemm_kb;
+      if (b + 1 < w.n_blocks) want[3 + 3 * b] = g_head_fill_row_kb;
+    }
+    n_pieces = plan_head_pieces(P, (D + 63) / 64, want, n_slots, pieces, kMaxPieces);
+    if (n_pieces <= 0) fill = false;
+  }
+  BD_REQUIRE(8 + 4 + 7 * w.n_blocks + 1 + n_pieces <= kStreamMaxOps);
 
   static thread_local StreamProgram prog;
   prog = StreamProgram{};
@@ -398,7 +465,7 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
     for (int j = 0; j < 6; ++j) prog.sched[i][j] = sched_host[i * 8 + j];
   int n = 0;
   auto gemm_op = [&](const void* W, const void* A, const void* bias, int N, int K, int ksplit, int epi, int act, void* out,
-                     long long ld, bool blocked) {
+                     long long ld, bool blocked) -> StreamOp& {
     StreamOp& op = prog.ops[n++];
     op = StreamOp{};
     op.kind = kOpGemm;
@@ -414,6 +481,7 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
     op.p2 = bias;
     op.o0 = out;
     op.l0 = ld;
+    return op;
   };
   auto row_op_ = [&](int sub) -> StreamOp& {
     StreamOp& op = prog.ops[n++];
@@ -423,6 +491,28 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
     op.wait_prev = 1;
     op.f0 = 1e-6f;
     return op;
+  };
+  // row ops read the modulation of THIS evaluation: buffer it & 1 when the fillers double-buffer it
+  auto mod_reader = [&](StreamOp& op) {
+    if (fill) {
+      op.flags |= kFlagParityIt;
+      op.l1 = static_cast<long long>(L.mod_bytes);
+    }
+  };
+  int next_piece = 0;
+  auto fill_slot = [&](int slot) {  // the adaLN pieces of evaluation it + 1 that hide the bubble at this point
+    while (fill && next_piece < n_pieces && pieces[next_piece].slot == slot) {
+      const HeadPiece& pc = pieces[next_piece++];
+      StreamOp& op = gemm_op(w.ada_w, base + L.y, w.ada_b, n_mod, D, 1, kEpiBias, kActNone, base + L.mod, n_mod, false);
+      op.wait_prev = 0;
+      op.flags |= kFlagFiller | kFlagAPerIt | kFlagParityNext | kFlagSkipLast;
+      op.i0 = 1;                                        // A = y[it + 1]
+      op.l1 = static_cast<long long>(L.mod_bytes);      // out = mod[(it + 1) & 1]
+      op.pc_pass = pc.pass;
+      op.pc_kb0 = pc.kb0;
+      op.pc_kbn = pc.kbn;
+      op.pc_flags = (pc.kb0 == 0 ? kPieceFirst : 0) | (pc.kb0 + pc.kbn == (D + 63) / 64 ? kPieceLast : 0);
+    }
   };
   __nv_bfloat16* mod = reinterpret_cast<__nv_bfloat16*>(base + L.mod);
   // ---- once per call ----
@@ -452,7 +542,17 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
   gemm_op(w.cond_w, base + L.condb, w.cond_b, D, w.Dz, 1, kEpiBias, kActNone, base + L.cemb, D, false);
   gemm_op(w.time2_w, base + L.th, w.time2_b, D, D, 1, kEpiBias, kActNone, base + L.temb, D, false);
   prog.ops[n - 1].i1 = S + 1;
-  {  // y of evaluation 0 (the y of evaluation i+1 is produced by evaluation i's SDE op)
+  if (fill) {
+    {  // y of EVERY evaluation, then the modulation of evaluation 0 (those of 1.. are filler pieces)
+      StreamOp& op = row_op_(kRowSiluAddAll);
+      op.p0 = base + L.temb;
+      op.p1 = base + L.cemb;
+      op.o0 = base + L.y;
+      op.l1 = static_cast<long long>(L.y_bytes);
+      op.N = D;
+    }
+    gemm_op(w.ada_w, base + L.y, w.ada_b, n_mod, D, 1, kEpiBias, kActNone, mod, n_mod, false);
+  } else {  // y of evaluation 0 (the y of evaluation i+1 is produced by evaluation i's SDE op)
     StreamOp& op = row_op_(kRowSiluAdd);
     op.p0 = base + L.temb;
     op.p1 = base + L.cemb;
@@ -461,11 +561,13 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
   }
   prog.n_pre = n;
   // ---- one evaluation + SDE step ----
-  // input_proj (needs xb) and the adaLN GEMM (needs y) both depend only on the previous SDE op: the second one skips the
-  // barrier of the first (wait_prev = -1), so the two weight streams run back to back
   gemm_op(w.input_proj_w, base + L.xb, w.input_proj_b, D, C, 1, kEpiBias, kActNone, base + L.h, D, false);
-  gemm_op(w.ada_w, base + L.y, w.ada_b, n_mod, D, 1, kEpiBias, kActNone, mod, n_mod, false);
-  prog.ops[n - 1].wait_prev = -1;
+  if (!fill) {
+    // input_proj (needs xb) and the adaLN GEMM (needs y) both depend only on the previous SDE op: the second one skips the
+    // barrier of the first (wait_prev = -1), so the two weight streams run back to back
+    gemm_op(w.ada_w, base + L.y, w.ada_b, n_mod, D, 1, kEpiBias, kActNone, mod, n_mod, false);
+    prog.ops[n - 1].wait_prev = -1;
+  }
   {
     StreamOp& op = row_op_(kRowLnMod);
     op.p0 = base + L.h;
@@ -476,8 +578,10 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
     op.l0 = n_mod;
     op.o0 = base + L.a;
     op.N = D;
+    mod_reader(op);
   }
-  const int switch_freq = w.n_blocks / w.n_ada;
+  fill_slot(0);
+  const int switch_freq = w.n_blocks / w.n_ada > 0 ? w.n_blocks / w.n_ada : 1;
   const int ks_wo = stream_ksplit_for(D, D, G), ks_w2 = stream_ksplit_for(D, w.hidden, G);
   const __nv_bfloat16* mf = mod + static_cast<long long>(w.n_ada) * 6 * D;
   for (int blk = 0; blk < w.n_blocks; ++blk) {
@@ -510,11 +614,14 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
       op.l0 = n_mod;
       op.o0 = base + L.a;
       op.N = D;
+      mod_reader(op);
     }
+    fill_slot(1 + 3 * blk);
     if (w.use_swiglu)
       gemm_op(bw.w1_w, base + L.a, bw.w1_b, 2 * w.hidden, D, 1, kEpiSwiglu8, 0, base + L.g, 0, true);
     else
       gemm_op(bw.w1_w, base + L.a, bw.w1_b, w.hidden, D, 1, kEpiBias, kActSilu, base + L.g, 0, true);
+    fill_slot(2 + 3 * blk);
     gemm_op(bw.w2_w, base + L.g, nullptr, D, w.hidden, ks_w2, kEpiPartial, 0, base + L.part, 0, false);
     {
       const bool last = blk + 1 == w.n_blocks;
@@ -544,8 +651,11 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
         op.i1 = C;
         op.i2 = w.out_sigmoid;
       }
+      mod_reader(op);
+      if (!last) fill_slot(3 + 3 * blk);
     }
   }
+  if (fill && next_piece != n_pieces) return BD_ERR_INVALID;  // every piece placed exactly once
   {
     StreamOp& op = row_op_(kRowSde);
     op.p0 = base + L.pred;
@@ -554,10 +664,12 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
     op.o1 = base + L.xb;
     op.o2 = x_out;
     op.N = C;
-    op.p4 = base + L.temb;  // + y of the next evaluation
-    op.p5 = base + L.cemb;
-    op.o3 = base + L.y;
-    op.i0 = D;
+    if (!fill) {
+      op.p4 = base + L.temb;  // + y of the next evaluation
+      op.p5 = base + L.cemb;
+      op.o3 = base + L.y;
+      op.i0 = D;
+    }
   }
   prog.n_body = n - prog.n_pre;
   prog.n_post = 0;
@@ -569,6 +681,30 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
 using namespace bd;
 
 extern "C" {
+
+// Filler policy of the persistent sampler: mode 0 = adaLN GEMM in line (round-1 program), 1 = as filler pieces of the
+// previous evaluation; row_kb / gemm_kb = wanted k-blocks per slot (<= 0: keep).
+int bd_head_set_fillers(int mode, int row_kb, int gemm_kb) {
+  BD_REQUIRE(mode == 0 || mode == 1);
+  g_head_fillers = mode;
+  if (row_kb > 0) g_head_fill_row_kb = row_kb;
+  if (gemm_kb > 0) g_head_fill_gemm_kb = gemm_kb;
+  return BD_OK;
+}
+
+// tests: the filler plan for P passes x KB k-blocks over slots of wanted sizes; out = n x {slot, pass, kb0, kbn}
+int bd_head_plan_pieces(int P, int KB, const int* want, int n_slots, int* out, int cap) {
+  BD_REQUIRE(want && out && P > 0 && KB > 0 && n_slots > 0 && cap > 0);
+  HeadPiece tmp[256];
+  const int n = plan_head_pieces(P, KB, want, n_slots, tmp, cap < 256 ? cap : 256);
+  for (int i = 0; i < n; ++i) {
+    out[4 * i] = tmp[i].slot;
+    out[4 * i + 1] = tmp[i].pass;
+    out[4 * i + 2] = tmp[i].kb0;
+    out[4 * i + 3] = tmp[i].kbn;
+  }
+  return n;
+}
 
 size_t bd_head_workspace_bytes(const bd_head_weights_t* w, int B, int pn, int cfg_mult, int S) {
   if (!w || B <= 0 || pn <= 0 || cfg_mult < 1 || cfg_mult > 2 || S < 0) return 0;

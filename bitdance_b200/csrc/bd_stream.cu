@@ -99,40 +99,77 @@ __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m,
 // ---------------------------------------------------------------------------------------------------------------------
 // row ops: executed by the 128 epilogue threads of CTA r for token row r
 // ---------------------------------------------------------------------------------------------------------------------
+// A row op is a chain of L2 round trips, not a bandwidth problem (there is no L1 left beside 226 KB of shared memory): the
+// round-1 version issued its loads iteration by iteration — every 16-byte store to the row (which may alias in the
+// compiler's eyes) fenced the next iteration's loads, the k-split loop had a run-time trip count, the LayerNorm affine
+// weights came as 4-byte loads — ~20 dependent round trips, 11 us per op (profiles/r01_rowop_experiments.txt). Here every
+// phase issues ALL its loads into registers first (compile-time vector count NV and split count), read-only operands go
+// through the non-coherent path (ld.global.nc may be hoisted above stores), and the row itself is kept as packed bf16
+// (it is bf16-rounded by construction) so that the operands of the next phase fit in registers while it is reduced.
 constexpr int kRowVec = 6;  // D <= 128 * 6 * 8 = 6144
 
-// LN statistics + modulate of a row held in registers; writes `a` blocked (or to smem floats when a_smem != nullptr).
-__device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, float (&v)[kRowVec][8], float sum, float* red,
+__device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float4 ldg_f4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+
+// LN statistics + modulate of a row held as packed bf16; writes `a` blocked (or to smem floats when a_smem != nullptr).
+template <int NV>
+__device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, const uint4 (&vb)[NV], float sum, float* red,
                                            const float* ln_w, const float* ln_b, float* a_smem) {
   const int D = op.N, nvec = D / 8;
+  const __nv_bfloat16* scale = reinterpret_cast<const __nv_bfloat16*>(op.p3) + static_cast<long long>(r) * op.l0;
+  const __nv_bfloat16* shift = reinterpret_cast<const __nv_bfloat16*>(op.p4) + static_cast<long long>(r) * op.l0;
+  // modulation + affine operands: in flight while the two block reductions run
+  uint4 scr[NV], shr[NV];
+  float4 lw[NV][2], lb[NV][2];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = tid + i * 128;
+    scr[i] = shr[i] = make_uint4(0, 0, 0, 0);
+    lw[i][0] = lw[i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+    lb[i][0] = lb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nvec) {
+      scr[i] = ldcg_u4(scale + c * 8);
+      shr[i] = ldcg_u4(shift + c * 8);
+      if (ln_w) {
+        lw[i][0] = ldg_f4(ln_w + c * 8);
+        lw[i][1] = ldg_f4(ln_w + c * 8 + 4);
+        lb[i][0] = ldg_f4(ln_b + c * 8);
+        lb[i][1] = ldg_f4(ln_b + c * 8 + 4);
+      }
+    }
+  }
   const float mean = epi_sum(sum, red, tid) / static_cast<float>(D);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kRowVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = tid + i * 128;
     if (c < nvec) {
+      float v[8];
+      bf16x8_to_f(vb[i], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
+        const float d = v[j] - mean;
         sq += d * d;
       }
     }
   }
   const float rstd = rsqrtf(epi_sum(sq, red, tid) / static_cast<float>(D) + op.f0);
-  const __nv_bfloat16* scale = reinterpret_cast<const __nv_bfloat16*>(op.p3) + static_cast<long long>(r) * op.l0;
-  const __nv_bfloat16* shift = reinterpret_cast<const __nv_bfloat16*>(op.p4) + static_cast<long long>(r) * op.l0;
   uint8_t* a = reinterpret_cast<uint8_t*>(op.o0);
 #pragma unroll
-  for (int i = 0; i < kRowVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = tid + i * 128;
     if (c < nvec) {
-      float sc[8], sh[8], o[8];
-      bf16x8_to_f(ldcg_u4(scale + c * 8), sc);
-      bf16x8_to_f(ldcg_u4(shift + c * 8), sh);
+      float v[8], sc[8], sh[8], o[8];
+      bf16x8_to_f(vb[i], v);
+      bf16x8_to_f(scr[i], sc);
+      bf16x8_to_f(shr[i], sh);
+      const float w8[8] = {lw[i][0].x, lw[i][0].y, lw[i][0].z, lw[i][0].w, lw[i][1].x, lw[i][1].y, lw[i][1].z, lw[i][1].w};
+      const float b8[8] = {lb[i][0].x, lb[i][0].y, lb[i][0].z, lb[i][0].w, lb[i][1].x, lb[i][1].y, lb[i][1].z, lb[i][1].w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float hn = (v[i][j] - mean) * rstd;
-        if (ln_w) hn = hn * ln_w[c * 8 + j] + ln_b[c * 8 + j];
+        float hn = (v[j] - mean) * rstd;
+        if (ln_w) hn = hn * w8[j] + b8[j];
         o[j] = hn * bf16_round(1.0f + sc[j]) + sh[j];
       }
       if (a_smem) {
@@ -143,6 +180,180 @@ __device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, f
       }
     }
   }
+}
+
+// h = bf16(h + bf16(bf16(sum_s partial_s + bias) * gate)), fixed summation order s = 0, 1, ... (deterministic); returns
+// the row as packed bf16 + its sum. Loads: two splits per batch, then [h, gate, bias] in one batch.
+template <int NV, int SC>  // SC: compile-time split count (0 = run time)
+__device__ __forceinline__ float row_splitk(const StreamOp& op, int M, int r, int tid, uint4 (&vb)[NV]) {
+  const int D = op.N, nvec = D / 8, S = SC > 0 ? SC : op.i0;
+  const float* part = reinterpret_cast<const float*>(op.p0) + static_cast<long long>(r) * D;
+  const long long sstride = static_cast<long long>(M) * D;
+  const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(op.p5);
+  const __nv_bfloat16* gate = reinterpret_cast<const __nv_bfloat16*>(op.p6) + static_cast<long long>(r) * op.l0;
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(op.o1) + static_cast<long long>(r) * D;
+  float acc[NV][8];
+  auto add_split = [&](int s, bool first) {
+    float4 x0[NV], x1[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = tid + i * 128;
+      x0[i] = x1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nvec) {
+        const float* q = part + s * sstride + c * 8;
+        x0[i] = ldcg_f4(q);
+        x1[i] = ldcg_f4(q + 4);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (first) {
+        acc[i][0] = x0[i].x; acc[i][1] = x0[i].y; acc[i][2] = x0[i].z; acc[i][3] = x0[i].w;
+        acc[i][4] = x1[i].x; acc[i][5] = x1[i].y; acc[i][6] = x1[i].z; acc[i][7] = x1[i].w;
+      } else {
+        acc[i][0] += x0[i].x; acc[i][1] += x0[i].y; acc[i][2] += x0[i].z; acc[i][3] += x0[i].w;
+        acc[i][4] += x1[i].x; acc[i][5] += x1[i].y; acc[i][6] += x1[i].z; acc[i][7] += x1[i].w;
+      }
+    }
+  };
+  // register budget (255 per thread, the op descriptor alone holds ~45): two splits' loads (80) + the sums (40) at a time,
+  // then the residual / gate / bias vectors (60) — three L2 round trips instead of ~20
+  if constexpr (SC > 0) {
+#pragma unroll
+    for (int s = 0; s < SC; ++s) {
+      if (s > 0 && (s & 1) == 0) compiler_fence();
+      add_split(s, s == 0);
+    }
+  } else {
+    add_split(0, true);
+    for (int s = 1; s < S; ++s) add_split(s, false);
+  }
+  compiler_fence();
+  uint4 hraw[NV], graw[NV], braw[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = tid + i * 128;
+    hraw[i] = graw[i] = braw[i] = make_uint4(0, 0, 0, 0);
+    if (c < nvec) {
+      hraw[i] = ldcg_u4(h + c * 8);
+      graw[i] = ldcg_u4(gate + c * 8);
+      braw[i] = ldg_u4(bias + c * 8);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = tid + i * 128;
+    vb[i] = make_uint4(0, 0, 0, 0);
+    if (c < nvec) {
+      float b[8], g[8], res[8], v[8];
+      bf16x8_to_f(braw[i], b);
+      bf16x8_to_f(graw[i], g);
+      bf16x8_to_f(hraw[i], res);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = bf16_round(bf16_round(acc[i][j] + b[j]) * g[j]);
+        v[j] = bf16_round(res[j] + y);
+        sum += v[j];
+      }
+      vb[i] = f_to_bf16x8(v);
+      *reinterpret_cast<uint4*>(h + c * 8) = vb[i];
+    }
+  }
+  return sum;
+}
+
+// final layer tail: a (bf16 values, fp32 in shared memory) -> o_c = bf16(sum_d a_d Wf[c,d] + bias_c); optional 2*sigmoid-1
+__device__ __forceinline__ void row_final_linear(const StreamOp& op, int M, int it, int r, int tid, const float* arow) {
+  const int D = op.N, C = op.i1;
+  const __nv_bfloat16* Wf = reinterpret_cast<const __nv_bfloat16*>(op.p1);
+  const __nv_bfloat16* bfin = reinterpret_cast<const __nv_bfloat16*>(op.p2);
+  float* pred = reinterpret_cast<float*>(op.o0);
+  float* trace = reinterpret_cast<float*>(op.o2);
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int c0 = warp * 8; c0 < C; c0 += 32) {  // 8 output channels per warp and round: 8 independent loads per step
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+#pragma unroll 2
+    for (int d = lane * 8; d < D; d += 256) {
+      uint4 raw[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        raw[u] = (c0 + u < C) ? ldg_u4(Wf + static_cast<long long>(c0 + u) * D + d) : make_uint4(0, 0, 0, 0);
+      const float4 a0 = *reinterpret_cast<const float4*>(arow + d), a1 = *reinterpret_cast<const float4*>(arow + d + 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float wv[8];
+        bf16x8_to_f(raw[u], wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[u] = fmaf(av[j], wv[j], acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+    if (lane < 8 && c0 + lane < C) {
+      float sel = acc[0];
+#pragma unroll
+      for (int u = 1; u < 8; ++u) sel = (lane == u) ? acc[u] : sel;
+      float o = bf16_round(sel + (bfin ? __bfloat162float(bfin[c0 + lane]) : 0.f));
+      if (op.i2) {
+        const float sg = bf16_round(1.0f / (1.0f + expf(-o)));
+        o = bf16_round(bf16_round(2.0f * sg) - 1.0f);
+      }
+      pred[static_cast<long long>(r) * C + c0 + lane] = o;
+      if (trace) trace[(static_cast<long long>(it) * M + r) * C + c0 + lane] = o;
+    }
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void row_op_ln_family(const StreamProgram& prog, const StreamOp& op, int it, int r, int tid,
+                                                 float* red, uint8_t* scratch) {
+  const int M = prog.M;
+  const float* ln_w = reinterpret_cast<const float*>(op.p1);
+  const float* ln_b = reinterpret_cast<const float*>(op.p2);
+  uint4 vb[NV];
+  if (op.sub == kRowLnMod) {
+    const int nvec = op.N / 8;
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(op.p0) + static_cast<long long>(r) * op.N;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = tid + i * 128;
+      vb[i] = c < nvec ? ldcg_u4(h + c * 8) : make_uint4(0, 0, 0, 0);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float v[8];
+      bf16x8_to_f(vb[i], v);  // zero beyond nvec
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[j];
+    }
+    row_ln_mod<NV>(op, r, tid, vb, sum, red, ln_w, ln_b, nullptr);
+    return;
+  }
+  // h = bf16(h + bf16(bf16(sum_s partial_s + bias) * gate));  then the LayerNorm-modulate that follows in the network
+  // (TransBlock.forward flow_head_parallel_x.py:242-252; FinalLayer.forward :169-173 for kRowFinal)
+  float sum;
+  if (op.i0 == 4) sum = row_splitk<NV, 4>(op, M, r, tid, vb);
+  else if (op.i0 == 2) sum = row_splitk<NV, 2>(op, M, r, tid, vb);
+  else if (op.i0 == 1) sum = row_splitk<NV, 1>(op, M, r, tid, vb);
+  else sum = row_splitk<NV, 0>(op, M, r, tid, vb);
+  if (op.sub == kRowSplitkLnMod) {
+    row_ln_mod<NV>(op, r, tid, vb, sum, red, ln_w, ln_b, nullptr);
+    return;
+  }
+  // final layer: LayerNorm without affine; a stays in shared memory (aliasing the A ring), then the 5120 -> C Linear
+  float* arow = reinterpret_cast<float*>(scratch);
+  row_ln_mod<NV>(op, r, tid, vb, sum, red, nullptr, nullptr, arow);
+  epi_bar();
+  row_final_linear(op, M, it, r, tid, arow);
+  epi_bar();  // arow (aliasing the A ring) is dead before anything else may touch it
 }
 
 __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp& op, int it, int r, int tid, float* red,
@@ -197,108 +408,56 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       }
       return;
     }
-    case kRowLnMod: {
+    case kRowSiluAddAll: {
+      // y[j] = bf16(silu(bf16(temb[j] + cemb[r]))) for EVERY evaluation j (all known before the first one: the timestep
+      // schedule is fixed and c does not change during a sampler call) -> o0 + j * l1, blocked. Lets the adaLN GEMM of
+      // evaluation j + 1 run as filler pieces inside evaluation j. The next temb row is fetched before the current one is
+      // stored (stores would otherwise fence the loads).
       if (r >= M) return;
       const int nvec = op.N / 8;
-      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(op.p0) + static_cast<long long>(r) * op.N;
-      float v[kRowVec][8];
-      float sum = 0.f;
+      const __nv_bfloat16* te = reinterpret_cast<const __nv_bfloat16*>(op.p0);
+      const __nv_bfloat16* ce = reinterpret_cast<const __nv_bfloat16*>(op.p1) + static_cast<long long>(r) * op.N;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(op.o0);
+      uint4 cer[kRowVec], cur[kRowVec], nxt[kRowVec];
 #pragma unroll
       for (int i = 0; i < kRowVec; ++i) {
         const int c = tid + i * 128;
+        cer[i] = cur[i] = nxt[i] = make_uint4(0, 0, 0, 0);
         if (c < nvec) {
-          bf16x8_to_f(ldcg_u4(h + c * 8), v[i]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sum += v[i][j];
+          cer[i] = ldcg_u4(ce + c * 8);
+          cur[i] = ldcg_u4(te + c * 8);
         }
       }
-      row_ln_mod(op, r, tid, v, sum, red, reinterpret_cast<const float*>(op.p1), reinterpret_cast<const float*>(op.p2), nullptr);
+      for (int j = 0; j < prog.n_iter; ++j) {
+        if (j + 1 < prog.n_iter) {
+#pragma unroll
+          for (int i = 0; i < kRowVec; ++i) {
+            const int c = tid + i * 128;
+            if (c < nvec) nxt[i] = ldcg_u4(te + static_cast<long long>(j + 1) * op.N + c * 8);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kRowVec; ++i) {
+          const int c = tid + i * 128;
+          if (c < nvec) {
+            float a[8], b[8], o[8];
+            bf16x8_to_f(cur[i], a);
+            bf16x8_to_f(cer[i], b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = siluf_(bf16_round(a[k] + b[k]));
+            *reinterpret_cast<uint4*>(dst + j * op.l1 + blk_off(r, c * 8)) = f_to_bf16x8(o);
+          }
+          cur[i] = nxt[i];
+        }
+      }
       return;
     }
+    case kRowLnMod:
     case kRowSplitkLnMod:
     case kRowFinal: {
-      // h = bf16(h + bf16(bf16(sum_s partial_s + bias) * gate));  then the LayerNorm-modulate that follows in the network
-      // (TransBlock.forward flow_head_parallel_x.py:242-252; FinalLayer.forward :169-173 for kRowFinal)
       if (r >= M) return;
-      const int D = op.N, nvec = D / 8, S = op.i0;
-      const float* part = reinterpret_cast<const float*>(op.p0);
-      const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(op.p5);
-      const __nv_bfloat16* gate = reinterpret_cast<const __nv_bfloat16*>(op.p6) + static_cast<long long>(r) * op.l0;
-      __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(op.o1) + static_cast<long long>(r) * D;
-      float v[kRowVec][8];
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < kRowVec; ++i) {
-        const int c = tid + i * 128;
-        if (c < nvec) {
-          float acc[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-          for (int s = 0; s < S; ++s) {  // fixed order: deterministic
-            const float* q = part + (static_cast<long long>(s) * M + r) * D + c * 8;
-            const float4 x0 = ldcg_f4(q), x1 = ldcg_f4(q + 4);
-            acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
-            acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
-          }
-          float b[8], g[8], res[8];
-          bf16x8_to_f(*reinterpret_cast<const uint4*>(bias + c * 8), b);
-          bf16x8_to_f(ldcg_u4(gate + c * 8), g);
-          bf16x8_to_f(ldcg_u4(h + c * 8), res);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float y = bf16_round(bf16_round(acc[j] + b[j]) * g[j]);
-            v[i][j] = bf16_round(res[j] + y);
-            sum += v[i][j];
-          }
-          *reinterpret_cast<uint4*>(h + c * 8) = f_to_bf16x8(v[i]);
-        }
-      }
-      if (op.sub == kRowSplitkLnMod) {
-        row_ln_mod(op, r, tid, v, sum, red, reinterpret_cast<const float*>(op.p1), reinterpret_cast<const float*>(op.p2), nullptr);
-        return;
-      }
-      // final layer: a (bf16 values) stays in shared memory; o_c = bf16(sum_d a_d Wf[c,d] + bias_c); optional 2*sigmoid-1
-      float* arow = reinterpret_cast<float*>(scratch);
-      row_ln_mod(op, r, tid, v, sum, red, nullptr, nullptr, arow);
-      epi_bar();
-      const int C = op.i1;
-      const __nv_bfloat16* Wf = reinterpret_cast<const __nv_bfloat16*>(op.p1);
-      const __nv_bfloat16* bfin = reinterpret_cast<const __nv_bfloat16*>(op.p2);
-      float* pred = reinterpret_cast<float*>(op.o0);
-      float* trace = reinterpret_cast<float*>(op.o2);
-      const int warp = tid >> 5, lane = tid & 31;
-      for (int c0 = warp * 4; c0 < C; c0 += 16) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int d = lane * 8; d < D; d += 256) {
-          uint4 raw[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            raw[u] = (c0 + u < C) ? *reinterpret_cast<const uint4*>(Wf + static_cast<long long>(c0 + u) * D + d)
-                                  : make_uint4(0, 0, 0, 0);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float wv[8];
-            bf16x8_to_f(raw[u], wv);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[u] = fmaf(arow[d + j], wv[j], acc[u]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-        }
-        if (lane < 4 && c0 + lane < C) {
-          float o = bf16_round(acc[lane] + (bfin ? __bfloat162float(bfin[c0 + lane]) : 0.f));
-          if (op.i2) {
-            const float sg = bf16_round(1.0f / (1.0f + expf(-o)));
-            o = bf16_round(bf16_round(2.0f * sg) - 1.0f);
-          }
-          pred[static_cast<long long>(r) * C + c0 + lane] = o;
-          if (trace) trace[(static_cast<long long>(it) * M + r) * C + c0 + lane] = o;
-        }
-      }
-      epi_bar();  // arow (aliasing the A ring) is dead before anything else may touch it
+      if (op.N == 5120) row_op_ln_family<5>(prog, op, it, r, tid, red, scratch);  // the 14B head: no predicated tail
+      else row_op_ln_family<kRowVec>(prog, op, it, r, tid, red, scratch);
       return;
     }
     case kRowSde: {  // sampling_x.py:24-41 with explicit round-to-nearest ops (torch rounds every op separately)
@@ -591,11 +750,14 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int kAccBufs = 3;            // TMEM accumulator buffers: 0 / 1 alternate over the passes of the dependent chain,
+constexpr uint32_t kTmemCols = 512;    //   2 collects the pieces of a filler pass (128 columns each; 512 allocated)
+
 struct StreamSmem {
   static constexpr int kRing = kStreamSlots * kStepBytes;
-  static constexpr int kBars = (2 * kStreamSlots + 4 + 1) * 8;  // rings, accumulators, + the epilogue warps' own bulk-copy barrier
-  static constexpr int kBias = 2 * 256;  // one pass's bias slice (<= 128 bf16) per accumulator buffer
-  static constexpr int kMisc = 256;      // barriers (<= 160 B), TMEM slot at +192, reduction scratch at +208
+  static constexpr int kBars = (2 * kStreamSlots + 2 * kAccBufs + 1) * 8;  // rings, accumulators, + the epilogue warps' own bulk-copy barrier
+  static constexpr int kBias = kAccBufs * 256;  // one pass's bias slice (<= 128 bf16) per accumulator buffer
+  static constexpr int kMisc = 256;      // barriers (<= 168 B), TMEM slot at +192, reduction scratch at +208
   static_assert(kBars <= 192, "barrier area");
   static constexpr int kTotal = kRing + kMisc + kBias + 1024 /*align slack*/;
 };
@@ -610,77 +772,6 @@ struct RingPos {  // position in a ring of n slots: slot index + how many times 
     }
   }
 };
-
-// The weight stream of one CTA as a flat sequence of steps (op after op, pass after pass, k rotation inside a pass): two
-// cursors walk it — the L2 prefetch cursor a fixed distance ahead of the shared-memory load cursor.
-struct WStream {
-  const StreamProgram& prog;
-  int G, c, total;
-  int q = -1, i = 0, t = 0;           // op sequence number, pass, step
-  int npass = 0, nsteps = 0, rot = 0, kbs = 0, N = 0;
-  StreamPart part{};
-  const uint8_t* w = nullptr;
-  const uint8_t* base = nullptr;      // first slot of the current pass
-  uint32_t kb_bytes = 0;
-  __device__ WStream(const StreamProgram& p, int G_, int c_, int total_) : prog(p), G(G_), c(c_), total(total_) {}
-  __device__ __forceinline__ bool next_op() {
-    for (++q; q < total; ++q) {
-      int idx, it;
-      if (q < prog.n_pre) { idx = q; it = 0; }
-      else {
-        const int b = q - prog.n_pre, nb = prog.n_body * prog.n_iter;
-        if (b < nb) { it = b / prog.n_body; idx = prog.n_pre + b % prog.n_body; }
-        else { idx = prog.n_pre + prog.n_body + (b - nb); it = prog.n_iter - 1; }
-      }
-      const StreamOp& op = prog.ops[idx];
-      if (op.kind != kOpGemm) continue;
-      if ((op.flags & kFlagSkipLast) && it == prog.n_iter - 1) continue;
-      part = stream_partition(op.N, op.K, op.ksplit, G, c);
-      if (part.units == 0) continue;
-      N = op.N;
-      w = reinterpret_cast<const uint8_t*>(op.p0);
-      npass = part.npass;
-      kbs = part.kbs;
-      nsteps = stream_steps(part.kbs);
-      rot = stream_k_rot(c, nsteps);
-      i = 0;
-      t = 0;
-      set_pass();
-      return true;
-    }
-    return false;
-  }
-  __device__ __forceinline__ void set_pass() {
-    const int wd = (stream_pass_u0(part, i + 1) - stream_pass_u0(part, i)) * 16;
-    kb_bytes = static_cast<uint32_t>(wd) * 128u;
-    base = w + stream_pass_offset(N, part, i) * 2048;
-  }
-  // address / size of the next step; false at the end of the program
-  __device__ __forceinline__ bool next(const uint8_t*& addr, uint32_t& bytes) {
-    if (q < 0 || t >= nsteps) {
-      if (q >= 0 && i + 1 < npass) {
-        ++i;
-        t = 0;
-        set_pass();
-      } else if (!next_op()) {
-        return false;
-      }
-    }
-    int st = rot + t;
-    if (st >= nsteps) st -= nsteps;
-    const int kbl = st * kKbPerStep;
-    const int nkb = min(kKbPerStep, kbs - kbl);
-    bytes = kb_bytes * static_cast<uint32_t>(nkb);  // the k-blocks of a pass are adjacent in HBM
-    addr = base + static_cast<long long>(kbl) * kb_bytes;
-    ++t;
-    return true;
-  }
-};
-
-// wait_prev: 1 = all earlier ops, 0 = none, -k = all earlier ops except the k most recent ones
-__device__ __forceinline__ unsigned int wait_target(int wait_prev, int q, int G) {
-  return static_cast<unsigned int>(G) * static_cast<unsigned int>(wait_prev < 0 ? max(q + wait_prev, 0) : q);
-}
 
 __device__ __forceinline__ void op_at(const StreamProgram& prog, int q, int& idx, int& it) {
   if (q < prog.n_pre) {
@@ -699,6 +790,123 @@ __device__ __forceinline__ void op_at(const StreamProgram& prog, int q, int& idx
   it = prog.n_iter - 1;
 }
 
+// Walks the program in order. mseq = the op's sequence number in the grid-barrier protocol = number of NON-filler ops
+// before it (fillers do not arrive, so they must not be counted by those who wait).
+struct OpCursor {
+  const StreamProgram& prog;
+  int total;
+  int q = -1, idx = 0, it = 0;
+  unsigned int mseq = 0;
+  __device__ OpCursor(const StreamProgram& p, int total_) : prog(p), total(total_) {}
+  __device__ __forceinline__ bool next() {
+    if (q >= 0 && !(prog.ops[idx].flags & kFlagFiller)) ++mseq;
+    if (++q >= total) return false;
+    op_at(prog, q, idx, it);
+    return true;
+  }
+};
+
+// The part of a GEMM op one CTA works on: passes [p0, p1) of its share, k-blocks [kb_first, kb_first + kbn) of the split.
+struct GemmWork {
+  StreamPart part;
+  int p0, p1, kb_first, kbn;
+  bool piece, first, last;
+  __device__ __forceinline__ bool any() const { return p1 > p0; }
+};
+__device__ __forceinline__ GemmWork gemm_work(const StreamOp& op, int G, int c) {
+  GemmWork w;
+  w.part = stream_partition(op.N, op.K, op.ksplit, G, c);
+  w.piece = op.pc_kbn > 0;
+  if (w.piece) {
+    const bool has = w.part.units > 0 && op.pc_pass < w.part.npass;
+    w.p0 = op.pc_pass;
+    w.p1 = has ? op.pc_pass + 1 : op.pc_pass;
+    w.kb_first = op.pc_kb0;
+    w.kbn = op.pc_kbn;
+    w.first = (op.pc_flags & kPieceFirst) != 0;
+    w.last = (op.pc_flags & kPieceLast) != 0;
+  } else {
+    w.p0 = 0;
+    w.p1 = w.part.units > 0 ? w.part.npass : 0;
+    w.kb_first = 0;
+    w.kbn = w.part.kbs;
+    w.first = w.last = true;
+  }
+  return w;
+}
+__device__ __forceinline__ bool op_skipped(const StreamProgram& prog, const StreamOp& op, int it) {
+  return (op.flags & kFlagSkipLast) && it == prog.n_iter - 1;
+}
+
+// The weight stream of one CTA as a flat sequence of steps (op after op, pass after pass, k rotation inside a pass): two
+// cursors walk it — the L2 prefetch cursor a fixed distance ahead of the shared-memory load cursor.
+struct WStream {
+  const StreamProgram& prog;
+  int G, c, total;
+  int q = -1, i = 0, t = 0;           // op sequence number, pass, step
+  int pass_end = 0, nsteps = 0, rot = 0, kbn = 0, kb_first = 0, N = 0;
+  StreamPart part{};
+  const uint8_t* w = nullptr;
+  const uint8_t* base = nullptr;      // first slot of the current pass
+  uint32_t kb_bytes = 0;
+  __device__ WStream(const StreamProgram& p, int G_, int c_, int total_) : prog(p), G(G_), c(c_), total(total_) {}
+  __device__ __forceinline__ bool next_op() {
+    for (++q; q < total; ++q) {
+      int idx, it;
+      op_at(prog, q, idx, it);
+      const StreamOp& op = prog.ops[idx];
+      if (op.kind != kOpGemm) continue;
+      if (op_skipped(prog, op, it)) continue;
+      const GemmWork gw = gemm_work(op, G, c);
+      if (!gw.any()) continue;
+      part = gw.part;
+      N = op.N;
+      w = reinterpret_cast<const uint8_t*>(op.p0);
+      i = gw.p0;
+      pass_end = gw.p1;
+      kb_first = gw.kb_first;
+      kbn = gw.kbn;
+      nsteps = stream_steps(kbn);
+      rot = stream_k_rot(c, nsteps);
+      t = 0;
+      set_pass();
+      return true;
+    }
+    return false;
+  }
+  __device__ __forceinline__ void set_pass() {
+    const int wd = (stream_pass_u0(part, i + 1) - stream_pass_u0(part, i)) * 16;
+    kb_bytes = static_cast<uint32_t>(wd) * 128u;
+    base = w + stream_pass_offset(N, part, i) * 2048;
+  }
+  // address / size of the next step; false at the end of the program
+  __device__ __forceinline__ bool next(const uint8_t*& addr, uint32_t& bytes) {
+    if (q < 0 || t >= nsteps) {
+      if (q >= 0 && i + 1 < pass_end) {
+        ++i;
+        t = 0;
+        set_pass();
+      } else if (!next_op()) {
+        return false;
+      }
+    }
+    int st = rot + t;
+    if (st >= nsteps) st -= nsteps;
+    const int kbl = st * kKbPerStep;
+    const int nkb = min(kKbPerStep, kbn - kbl);
+    bytes = kb_bytes * static_cast<uint32_t>(nkb);  // the k-blocks of a pass are adjacent in HBM
+    addr = base + static_cast<long long>(kb_first + kbl) * kb_bytes;
+    ++t;
+    return true;
+  }
+};
+
+// wait_prev: 1 = all earlier (non-filler) ops, 0 = none, -k = all earlier ops except the k most recent ones
+__device__ __forceinline__ unsigned int wait_target(int wait_prev, unsigned int mseq, int G) {
+  const unsigned int n = wait_prev < 0 ? (mseq > static_cast<unsigned int>(-wait_prev) ? mseq + wait_prev : 0u) : mseq;
+  return static_cast<unsigned int>(G) * n;
+}
+
 #define BD_STAMP(q_, e_)                                                                             \
   do {                                                                                               \
     if (prog.dbg && (q_) < prog.dbg_ops) prog.dbg[(static_cast<long long>(q_) * G + c) * 8 + (e_)] = gtimer(); \
@@ -715,8 +923,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
   uint64_t* full_a = empty_w + kStreamWSlots;
   uint64_t* empty_a = full_a + kStreamASlots;
   uint64_t* acc_full = empty_a + kStreamASlots;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* aux_bar = acc_empty + 2;
+  uint64_t* acc_empty = acc_full + kAccBufs;
+  uint64_t* aux_bar = acc_empty + kAccBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + StreamSmem::kRing + 192);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);
   __nv_bfloat16* bias_s = reinterpret_cast<__nv_bfloat16*>(smem + StreamSmem::kRing + StreamSmem::kMisc);  // 16-byte aligned
@@ -735,14 +943,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
       mbar_init(&full_a[s], 1);
       mbar_init(&empty_a[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kAccBufs; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
     }
     mbar_init(aux_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -755,9 +963,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
       WStream ld(prog, G, c, total), pf(prog, G, c, total);
       const uint8_t* addr;
       uint32_t bytes;
-      // L2 prefetch cursor: `pf_steps` steps (~28 KB each) ahead of the load cursor. When the ring is full and this thread
-      // blocks — the other warps are in an epilogue, a row op or a grid barrier — HBM keeps streaming the next weights into
-      // L2 (148 CTAs x pf_steps x 28 KB, well inside the 126 MB), and the ring then refills from L2 faster than from HBM.
+      // optional L2 prefetch cursor `pf_steps` steps ahead of the load cursor (measured slower: off by default)
       bool pf_live = prog.pf_steps > 0;
       for (int k = 0; pf_live && k < prog.pf_steps; ++k) {
         pf_live = pf.next(addr, bytes);
@@ -781,33 +987,34 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
     // ===================== A producer: waits for the op's grid-wide dependency, then streams the blocked activations
     if (elect_one()) {
       RingPos ar(kStreamASlots);
-      for (int q = 0; q < total; ++q) {
-        int idx, it;
-        op_at(prog, q, idx, it);
-        const StreamOp& op = prog.ops[idx];
+      OpCursor cur(prog, total);
+      while (cur.next()) {
+        const StreamOp& op = prog.ops[cur.idx];
         if (op.kind != kOpGemm) continue;
-        if ((op.flags & kFlagSkipLast) && it == prog.n_iter - 1) continue;
-        const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
-        if (part.units == 0) continue;
+        if (op_skipped(prog, op, cur.it)) continue;
+        const GemmWork gw = gemm_work(op, G, c);
+        if (!gw.any()) continue;
         if (op.wait_prev) {
-          grid_wait(prog.sync, wait_target(op.wait_prev, q, G), static_cast<unsigned int>(prog.poll_ns));
+          grid_wait(prog.sync, wait_target(op.wait_prev, cur.mseq, G), static_cast<unsigned int>(prog.poll_ns));
           fence_proxy_async_all();  // other CTAs' generic-proxy stores -> this thread's async-proxy (bulk copy) reads
         }
-        BD_STAMP(q, 0);
-        const int nsteps = stream_steps(part.kbs);
+        BD_STAMP(cur.q, 0);
+        const int nsteps = stream_steps(gw.kbn);
         const int rot = stream_k_rot(c, nsteps);
         const uint8_t* abase = reinterpret_cast<const uint8_t*>(op.p1);
-        for (int i = 0; i < part.npass; ++i) {
+        if (op.flags & kFlagAPerIt) abase += static_cast<long long>(cur.it + op.i0) * ((op.K + 63) / 64) * kSlotBytes;
+        abase += static_cast<long long>(gw.part.kb0 + gw.kb_first) * kSlotBytes;
+        for (int i = gw.p0; i < gw.p1; ++i) {
           for (int t = 0; t < nsteps; ++t) {
             int st = rot + t;
             if (st >= nsteps) st -= nsteps;
             const int kbl = st * kKbPerStep;
-            const uint32_t bytes = static_cast<uint32_t>(min(kKbPerStep, part.kbs - kbl)) * kSlotBytes;
+            const uint32_t bytes = static_cast<uint32_t>(min(kKbPerStep, gw.kbn - kbl)) * kSlotBytes;
             const uint32_t s = ar.slot;
             if (ar.round > 0) mbar_wait(&empty_a[s], (ar.round & 1u) ^ 1u);
             mbar_expect_tx(&full_a[s], bytes);
-            bulk_g2s(smem_a + s * kStepBytes, abase + static_cast<long long>(part.kb0 + kbl) * kSlotBytes, bytes,
-                     &full_a[s], kEvictLast);
+            bulk_g2s(smem_a + s * kStepBytes, abase + static_cast<long long>(kbl) * kSlotBytes, bytes, &full_a[s],
+                     kEvictLast);
             ar.advance();
           }
         }
@@ -817,50 +1024,62 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
     // ===================== MMA issuer =====================
     if (elect_one()) {
       RingPos wr(kStreamWSlots), ar(kStreamASlots);
-      uint32_t pi = 0;
-      for (int q = 0; q < total; ++q) {
-        int idx, it;
-        op_at(prog, q, idx, it);
-        const StreamOp& op = prog.ops[idx];
+      uint32_t pi = 0, pf = 0;  // passes of the dependent chain (buffers 0 / 1), completed filler accumulations (buffer 2)
+      OpCursor cur(prog, total);
+      while (cur.next()) {
+        const StreamOp& op = prog.ops[cur.idx];
         if (op.kind != kOpGemm) continue;
-        if ((op.flags & kFlagSkipLast) && it == prog.n_iter - 1) continue;
-        const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
-        if (part.units == 0) continue;
-        for (int i = 0; i < part.npass; ++i) {
-          const int w = (stream_pass_u0(part, i + 1) - stream_pass_u0(part, i)) * 16;
+        if (op_skipped(prog, op, cur.it)) continue;
+        const GemmWork gw = gemm_work(op, G, c);
+        if (!gw.any()) continue;
+        const int q = cur.q;
+        for (int i = gw.p0; i < gw.p1; ++i) {
+          const int w = (stream_pass_u0(gw.part, i + 1) - stream_pass_u0(gw.part, i)) * 16;
           const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(w));
-          const uint32_t buf = pi & 1u;
-          if (pi >= 2) mbar_wait(&acc_empty[buf], ((pi >> 1) & 1u) ^ 1u);
+          const uint32_t buf = gw.piece ? 2u : (pi & 1u);
+          if (gw.piece) {
+            if (gw.first && pf >= 1) mbar_wait(&acc_empty[2], (pf & 1u) ^ 1u);
+          } else if (pi >= 2) {
+            mbar_wait(&acc_empty[buf], ((pi >> 1) & 1u) ^ 1u);
+          }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * 128u;
-          const int nsteps = stream_steps(part.kbs);
+          const int nsteps = stream_steps(gw.kbn);
           const int rot = stream_k_rot(c, nsteps);
           const uint32_t kb_bytes = static_cast<uint32_t>(w) * 128u;
+          const uint32_t keep = gw.first ? 0u : 1u;  // later pieces of a pass accumulate onto the earlier ones
           for (int t = 0; t < nsteps; ++t) {
             int st = rot + t;
             if (st >= nsteps) st -= nsteps;
-            const int nkb = min(kKbPerStep, part.kbs - st * kKbPerStep);
+            const int nkb = min(kKbPerStep, gw.kbn - st * kKbPerStep);
             const uint32_t sw = wr.slot, sa = ar.slot;
             mbar_wait(&full_w[sw], wr.round & 1u);
             mbar_wait(&full_a[sa], ar.round & 1u);
             tc_fence_after();
-            if (i == 0 && t == 0) BD_STAMP(q, 1);
+            if (i == gw.p0 && t == 0) BD_STAMP(q, 1);
             const uint32_t a_addr = smem_u32(smem_a + sa * kStepBytes);
             const uint32_t w_addr = smem_u32(smem_w + sw * kStepBytes);
             for (int kk = 0; kk < nkb; ++kk) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + kk * kSlotBytes + k * 32),
-                          umma_desc_k_sw128(w_addr + kk * kb_bytes + k * 32), idesc, (t | kk | k) != 0 ? 1u : 0u);
+                          umma_desc_k_sw128(w_addr + kk * kb_bytes + k * 32), idesc, (t | kk | k) != 0 ? 1u : keep);
             }
             umma_commit(&empty_w[sw]);
             umma_commit(&empty_a[sa]);
             wr.advance();
             ar.advance();
           }
-          umma_commit(&acc_full[buf]);
-          if (i == part.npass - 1) BD_STAMP(q, 2);
-          ++pi;
+          if (gw.piece) {
+            if (gw.last) {
+              umma_commit(&acc_full[2]);
+              ++pf;
+            }
+          } else {
+            umma_commit(&acc_full[buf]);
+            ++pi;
+          }
+          if (i == gw.p1 - 1) BD_STAMP(q, 2);
         }
       }
     }
@@ -870,14 +1089,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
     const int lane = tid & 31;
     const int qd = warp & 3;
     const int m = qd * 32 + lane;
-    uint32_t pi = 0, aux_uses = 0;
-    for (int q = 0; q < total; ++q) {
-      int idx, it;
-      op_at(prog, q, idx, it);
+    uint32_t pi = 0, pf = 0, aux_uses = 0;
+    OpCursor cur(prog, total);
+    while (cur.next()) {
+      const int q = cur.q, it = cur.it;
       // by value: the descriptor lives in registers for the whole op. (Reading it through the kernel-parameter bank with a
       // run-time index inside the per-element epilogue loops cost ~3 us per 32-column chunk: measured 11 us -> 1 us.)
-      StreamOp op = prog.ops[idx];
-      const bool skipped = (op.flags & kFlagSkipLast) && it == prog.n_iter - 1;
+      StreamOp op = prog.ops[cur.idx];
+      const bool skipped = op_skipped(prog, op, it);
+      const bool filler = (op.flags & kFlagFiller) != 0;
       if ((op.flags & kFlagParityIt) ? (it & 1) : ((op.flags & kFlagParityNext) ? ((it + 1) & 1) : 0)) {
         if (op.kind == kOpGemm) {
           op.o0 = reinterpret_cast<uint8_t*>(op.o0) + op.l1;  // double-buffered GEMM output
@@ -888,21 +1108,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         }
       }
       if (skipped) {
-        // nothing to do, but the arrival below keeps the cumulative barrier count in step
+        // nothing to do, but (non-filler ops) the arrival below keeps the cumulative barrier count in step
       } else if (op.kind == kOpGemm) {
-        const StreamPart part = stream_partition(op.N, op.K, op.ksplit, G, c);
+        const GemmWork gw = gemm_work(op, G, c);
         const int rows = op.i1 > 0 ? op.i1 : prog.M;  // valid token rows of this op
-        if (part.units == 0 && op.wait_prev) {
+        if (!gw.any() && op.wait_prev && !filler) {
           // a CTA without work must not run ahead: the arrival counter is cumulative, so every CTA has to pass every
           // dependency (CTAs with work do so through their A producer -> MMA -> accumulator chain)
-          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, q, G), static_cast<unsigned int>(prog.poll_ns));
+          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, cur.mseq, G), static_cast<unsigned int>(prog.poll_ns));
           epi_bar();
         }
-        for (int i = 0; i < part.npass; ++i) {
-          const int u0 = stream_pass_u0(part, i);
-          const int w = (stream_pass_u0(part, i + 1) - u0) * 16;
-          const int n0 = (part.unit0 + u0) * 16;
-          const uint32_t buf = pi & 1u;
+        const bool run_epi = !gw.piece || gw.last;  // earlier pieces of a pass only accumulate
+        for (int i = gw.p0; run_epi && i < gw.p1; ++i) {
+          const int u0 = stream_pass_u0(gw.part, i);
+          const int w = (stream_pass_u0(gw.part, i + 1) - u0) * 16;
+          const int n0 = (gw.part.unit0 + u0) * 16;
+          const uint32_t buf = gw.piece ? 2u : (pi & 1u);
+          const uint32_t par = gw.piece ? (pf & 1u) : ((pi >> 1) & 1u);
           // bias slice of this pass -> shared memory while the MMAs are still running (a global load per chunk after the
           // accumulator is ready would put an L2 round trip — there is no L1 left — on the dependency path)
           const __nv_bfloat16* bias_sm = nullptr;
@@ -913,9 +1135,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
             epi_bar();
             bias_sm = bias_s + buf * 128;
           }
-          mbar_wait(&acc_full[buf], (pi >> 1) & 1u);
+          mbar_wait(&acc_full[buf], par);
           tc_fence_after();
-          if (tid == 0 && i == part.npass - 1) BD_STAMP(q, 3);
+          if (tid == 0 && i == gw.p1 - 1) BD_STAMP(q, 3);
           const uint32_t tbase = tmem_base + buf * 128u + (static_cast<uint32_t>(qd * 32) << 16);
           // 32-column chunks start at packed columns that are multiples of 32, so that every store is whole 32-byte
           // sectors; a pass that starts / ends mid-way gets a 16-column chunk at that edge
@@ -927,7 +1149,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
             float acc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-            gemm_epi_chunk<16>(op, rows, m, n0 + cc, acc, part.split, prog.dbg_mode, bias_sm ? bias_sm + cc : nullptr);
+            gemm_epi_chunk<16>(op, rows, m, n0 + cc, acc, gw.part.split, prog.dbg_mode, bias_sm ? bias_sm + cc : nullptr);
           };
           if ((n0 & 31) != 0) {
             chunk16(0);
@@ -937,22 +1159,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
             uint32_t v[32];
             tmem_ld_32x32(tbase + static_cast<uint32_t>(col), v);
             tmem_ld_wait();
-            if (tid == 0 && i == part.npass - 1 && col <= 16) BD_STAMP(q, 6);
+            if (tid == 0 && i == gw.p1 - 1 && col <= 16) BD_STAMP(q, 6);
             float acc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-            gemm_epi_chunk<32>(op, rows, m, n0 + col, acc, part.split, prog.dbg_mode, bias_sm ? bias_sm + col : nullptr);
-            if (tid == 0 && i == part.npass - 1 && col <= 16) BD_STAMP(q, 7);
+            gemm_epi_chunk<32>(op, rows, m, n0 + col, acc, gw.part.split, prog.dbg_mode, bias_sm ? bias_sm + col : nullptr);
+            if (tid == 0 && i == gw.p1 - 1 && col <= 16) BD_STAMP(q, 7);
           }
           if (col < w) chunk16(col);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
-          ++pi;
+          if (gw.piece) ++pf;
+          else ++pi;
         }
       } else {
         if (op.wait_prev) {
-          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, q, G), static_cast<unsigned int>(prog.poll_ns));
+          if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, cur.mseq, G), static_cast<unsigned int>(prog.poll_ns));
           epi_bar();
         }
         if (op.kind == kOpRow) {
@@ -968,6 +1191,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         // generic-proxy writes to the A ring (attention tiles / final row) before later async-proxy (bulk copy) writes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
+      if (filler) continue;  // outside the barrier protocol: its consumers sit behind a later full barrier
       // ---- this CTA's part of op q is complete: publish ----
       if (tid == 0) BD_STAMP(q, 4);
       epi_bar();
@@ -980,7 +1204,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -1053,10 +1277,14 @@ int stream_launch(const StreamProgram& prog_in, cudaStream_t stream) {
     prog.w_slots = g_stream_w_slots;
     prog.a_slots = g_stream_a_slots;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    BD_CUDA_TRY(cudaFuncSetAttribute(bd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamSmem::kTotal));
-    attr_set = true;
+  {  // the attribute is per device (a process may drive several GPUs)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    BD_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      BD_CUDA_TRY(cudaFuncSetAttribute(bd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamSmem::kTotal));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   BD_CUDA_TRY(cudaMemsetAsync(prog.sync, 0, sizeof(unsigned int), stream));
   cudaLaunchConfig_t cfg{};
@@ -1185,6 +1413,62 @@ int bd_stream_gemm(const void* A_blocked, const void* W_packed, int64_t w_stride
     op.o0 = out;
     op.l0 = ld_out;
   }
+  return stream_launch(prog, static_cast<cudaStream_t>(stream));
+}
+
+int bd_stream_gemm_filler(const void* A_blocked, const void* W_main, const void* W_fill, const void* bias_fill,
+                          void* out_main, void* out_fill, int M, int N, int K, int n_ctas, int n_slices, int repeat,
+                          void* sync, bd_stream_t stream) {
+  BD_REQUIRE(A_blocked && W_main && W_fill && out_main && out_fill && sync && M > 0 && M <= 128 && N > 0 && (N % 16) == 0);
+  BD_REQUIRE(K > 0 && n_ctas > 0 && n_slices >= 1 && repeat >= 1 && repeat <= kStreamMaxIter);
+  const int KB = (K + 63) / 64, nsteps = stream_steps(KB);
+  BD_REQUIRE(n_slices <= nsteps);
+  int P = 0;
+  for (int c = 0; c < n_ctas; ++c) {
+    const StreamPart p = stream_partition(N, K, 1, n_ctas, c);
+    P = p.npass > P ? p.npass : P;
+  }
+  BD_REQUIRE(1 + P * n_slices <= kStreamMaxOps);
+  static StreamProgram prog;
+  prog = StreamProgram{};
+  prog.n_pre = 0;
+  prog.n_iter = repeat;
+  prog.n_post = 0;
+  prog.M = M;
+  prog.n_ctas = n_ctas;
+  prog.cfg_mult = 1;
+  prog.sync = static_cast<unsigned int*>(sync);
+  int n = 0;
+  auto base_op = [&](const void* W, const void* bias, void* out) -> StreamOp& {
+    StreamOp& op = prog.ops[n++];
+    op = StreamOp{};
+    op.kind = kOpGemm;
+    op.sub = kEpiBias;
+    op.N = N;
+    op.K = K;
+    op.ksplit = 1;
+    op.wait_prev = 1;
+    op.p0 = W;
+    op.p1 = A_blocked;
+    op.p2 = bias;
+    op.o0 = out;
+    op.l0 = N;
+    return op;
+  };
+  base_op(W_main, nullptr, out_main);
+  for (int pass = 0; pass < P; ++pass) {
+    for (int j = 0; j < n_slices; ++j) {
+      const int s0 = (j * nsteps) / n_slices, s1 = ((j + 1) * nsteps) / n_slices;
+      StreamOp& op = base_op(W_fill, bias_fill, out_fill);
+      op.wait_prev = 0;
+      op.flags |= kFlagFiller;
+      op.pc_pass = pass;
+      op.pc_kb0 = s0 * kKbPerStep;
+      op.pc_kbn = (s1 * kKbPerStep < KB ? s1 * kKbPerStep : KB) - op.pc_kb0;
+      op.pc_flags = (j == 0 ? kPieceFirst : 0) | (j == n_slices - 1 ? kPieceLast : 0);
+    }
+  }
+  prog.n_body = n;
   return stream_launch(prog, static_cast<cudaStream_t>(stream));
 }
 

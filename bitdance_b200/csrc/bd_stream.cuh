@@ -34,11 +34,16 @@ constexpr int kStepBytes = kKbPerStep * kSlotBytes;
 constexpr int kStreamSlots = 7;          // shared-memory ring slots (32 KB each) in total (W ring + A ring)
 constexpr int kStreamWSlotsDefault = 5;
 constexpr int kStreamASlotsDefault = 2;
-constexpr int kStreamMaxOps = 128;
+constexpr int kStreamMaxOps = 160;  // the program travels as a kernel parameter (< 32 KB)
 constexpr int kStreamMaxIter = 104;
 
 enum : int { kOpGemm = 0, kOpRow = 1, kOpAttn = 2 };
-enum : int { kFlagBlocked = 1, kFlagParityIt = 2, kFlagParityNext = 4, kFlagSkipLast = 8 };
+enum : int {
+  kFlagBlocked = 1, kFlagParityIt = 2, kFlagParityNext = 4, kFlagSkipLast = 8,
+  kFlagFiller = 16,   // GEMM op outside the grid-barrier sequence (see "fillers" below)
+  kFlagAPerIt = 32,   // GEMM op: the A operand of iteration `it` is p1 + (it + i0) * blocked bytes of K
+};
+enum : int { kPieceFirst = 1, kPieceLast = 2 };
 enum : int { kEpiBias = 0, kEpiSwiglu8 = 1, kEpiPartial = 2 };
 enum : int {
   kRowCastCond = 0,   // fp32 [M, K] -> blocked bf16
@@ -51,6 +56,7 @@ enum : int {
   kRowSde = 7,        // Euler–Maruyama / last Euler step on x; xb for the next evaluation
   kRowLlmRms = 8,     // Qwen3 RMSNorm of an fp32 residual row -> blocked bf16
   kRowLlmResRms = 9,  // residual += bf16(sum partials); then RMSNorm -> blocked bf16, or the final norm (+ pos table) -> fp32
+  kRowSiluAddAll = 10,// kRowSiluAdd for EVERY iteration at once: y[it] = silu(temb[it] + cemb[r]) -> o0 + it * l1 (blocked)
 };
 
 // One op. Field meaning per kind:
@@ -60,6 +66,16 @@ enum : int {
 //        (bit1) or `it + 1` (bit2) is odd; flags bit3: the op is skipped in the last iteration (it prepares the next one).
 //  wait_prev = 0 on a GEMM makes it a FILLER: its operands were complete long before, so its weight stream and MMAs
 //        overlap the epilogue / row op / barrier of the ops around it (the head's adaLN GEMM of the next evaluation).
+//  FILLERS (kFlagFiller, wait_prev = 0): GEMM work that depends on nothing the surrounding ops compute (the head's adaLN
+//        modulation of the NEXT evaluation). A filler does not take part in the grid barrier (no arrival, not counted in the
+//        sequence numbers the other ops wait for); its result is consumed only after a later full barrier, which every CTA
+//        passes after its own fillers (ops are processed in program order). A filler may be a PIECE of a GEMM
+//        (pc_kbn > 0): pass `pc_pass` of the CTA's share, k-blocks [pc_kb0, pc_kb0 + pc_kbn) only, accumulated in a third
+//        TMEM buffer across the pieces of that pass (pc_flags: kPieceFirst zero-initialises, kPieceLast runs the epilogue).
+//        Pieces are sized to the bubbles of the dependent chain (a row op, an op boundary): the MMA warp and the weight
+//        stream stay busy while the epilogue warps run the row op / wait for the grid barrier. Because the A ring doubles
+//        as scratch of the attention / final-row executors, a filler must never sit between a GEMM and such an op in GEMM
+//        order (the host program builder guarantees it).
 //  ROW:  sub = row kind; pointers documented at each row function
 //  ATTN: p0 = qkv row-major bf16 [M, 3D], o0 = out blocked bf16, N = D, K = head_dim
 struct StreamOp {
@@ -79,6 +95,7 @@ struct StreamOp {
   long long l0, l1;
   float f0;
   int i0, i1, i2;
+  int pc_pass, pc_kb0, pc_kbn, pc_flags;  // piece of a GEMM (pc_kbn > 0), see FILLERS
 };
 
 struct StreamProgram {

@@ -326,3 +326,25 @@ def stream_gemm(a: torch.Tensor, ws: "StreamWeight | list[StreamWeight]", *, epi
     if kind != 2 and out_blocked:
         return from_blocked(out, M, n_out)
     return out
+
+
+def stream_gemm_filler(a: torch.Tensor, w_main: StreamWeight, w_fill: StreamWeight, *, n_slices: int, repeat: int = 1):
+    """tests: ``repeat`` x {main GEMM; the second GEMM as filler pieces (n_slices k-ranges per pass, third TMEM buffer,
+    outside the grid-barrier protocol)} in one persistent launch. Returns (out_main, out_fill) [M, N] bf16."""
+    lib = _lib.load()
+    M = a.shape[0]
+    ab = to_blocked(a)
+    N, K, dev = w_main.N, w_main.K, w_main.data.device
+    assert (w_fill.N, w_fill.K) == (N, K) and w_main.ksplit == 1 and w_fill.ksplit == 1
+    out_main = torch.zeros((M, N), dtype=torch.bfloat16, device=dev)
+    out_fill = torch.zeros((M, N), dtype=torch.bfloat16, device=dev)
+    sync = torch.zeros(16, dtype=torch.int32, device=dev)
+    check(lib.bd_stream_gemm_filler(ptr(ab), ptr(w_main.data), ptr(w_fill.data), ptr(w_fill.bias), ptr(out_main),
+                                    ptr(out_fill), M, N, K, w_main.n_ctas, n_slices, repeat, ptr(sync), stream_ptr()),
+          "bd_stream_gemm_filler")
+    return out_main, out_fill
+
+
+def head_set_fillers(mode: int, row_kb: int = 0, gemm_kb: int = 0) -> None:
+    """Program policy of the persistent head sampler (``bd_head_set_fillers``)."""
+    check(_lib.load().bd_head_set_fillers(int(mode), int(row_kb), int(gemm_kb)), "bd_head_set_fillers")

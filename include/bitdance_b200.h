@@ -179,6 +179,16 @@ size_t bd_head_workspace_bytes(const bd_head_weights_t* w, int B, int pn, int cf
 /* tests / debugging: byte offsets of the named regions inside the workspace (xb, h, ... in the order documented in
  * csrc/bd_head.cu for the weights' layout kind); returns how many were written (<= cap). */
 int bd_head_ws_offsets(const bd_head_weights_t* w, int B, int pn, int cfg_mult, int S, size_t* out, int cap);
+/* Program policy of the persistent sampler. mode 1 (default): the adaLN-modulation GEMM of evaluation i + 1 (it depends
+ * on t and c only, flow_head_parallel_x.py:330-336) is cut into k-sliced pieces that run as FILLERS inside evaluation i,
+ * in the bubbles of the dependent chain (row ops, op boundaries) — see csrc/bd_stream.cuh; mode 0: in line at the start
+ * of every evaluation (the round-1 program). row_kb / gemm_kb: wanted piece size (k-blocks of 128 rows x 64) in a slot
+ * that hides a row op / a GEMM -> GEMM boundary; <= 0 keeps the current value. Results are identical in both modes up to
+ * the fp32 accumulation order of that one GEMM. */
+int bd_head_set_fillers(int mode, int row_kb, int gemm_kb);
+/* tests: the piece plan (host arithmetic only) for a GEMM of P passes x KB k-blocks per CTA and n_slots bubbles of wanted
+ * sizes want[]: out = n x {slot, pass, kb0, kbn}; returns n (< 0: does not fit `cap`). */
+int bd_head_plan_pieces(int P, int KB, const int* want, int n_slots, int* out, int cap);
 
 /* ------------------------------------------------------------------------------------------------
  * Qwen3 decoder stack with a paged KV cache
@@ -310,6 +320,13 @@ int bd_stream_pack_weight(const void* W, int64_t ldw, int N, int K, int ksplit, 
 int bd_stream_gemm(const void* A_blocked, const void* W_packed, int64_t w_stride_bytes, int n_w, const void* bias_packed,
                    void* out, int64_t ld_out, int M, int N, int K, int ksplit, int epi, int act, int out_blocked,
                    int n_ctas, int repeat, void* sync, bd_stream_t stream);
+
+/* tests: `repeat` x { one main GEMM op (W_main, bf16 row-major out_main [M, N]); then the GEMM (W_fill, bias_fill) ->
+ * out_fill [M, N] executed as FILLER pieces: every pass of every CTA cut into n_slices k-ranges accumulated in the third
+ * TMEM buffer, outside the grid-barrier protocol }. Both weights [N, K], ksplit 1, same A. */
+int bd_stream_gemm_filler(const void* A_blocked, const void* W_main, const void* W_fill, const void* bias_fill,
+                          void* out_main, void* out_fill, int M, int N, int K, int n_ctas, int n_slices, int repeat,
+                          void* sync, bd_stream_t stream);
 
 /* ---- measurement only (scripts/stream_probe.py; not on the product path, replaces nothing in the reference) ----
  * Streams n_ctas * w_per_cta bytes of `w` HBM -> shared memory through the same bulk-copy/mbarrier ring the GEMM uses

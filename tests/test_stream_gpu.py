@@ -105,6 +105,67 @@ def test_stream_gemm_chain_of_weights_and_repeat():
     assert (out - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item() + 1e-3
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,n_slices,repeat", [
+    (128, 148 * 128 * 2 + 160, 1024, 3, 2),   # two passes per CTA (+ a ragged tail), 3 pieces per pass
+    (128, 4096, 512 + 64, 2, 3),              # odd number of k-blocks: the last slice is short
+    (64, 2048, 256, 1, 1),                    # one piece = the whole pass
+    (128, 1024, 2048, 16, 2),                 # one ring step per piece
+])
+def test_stream_filler_pieces(M, N, K, n_slices, repeat):
+    """A GEMM executed as FILLER pieces (k-slices of each pass accumulated in the third TMEM buffer, outside the grid
+    barrier) between the ops of a dependent chain gives the result of the whole-op GEMM; the chain is undisturbed."""
+    from bitdance_b200 import ops
+    torch.manual_seed(4)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w1 = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    w2 = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    b2 = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16)
+    p1, p2 = ops.stream_pack_weight(w1, None), ops.stream_pack_weight(w2, b2)
+    o1, o2 = ops.stream_gemm_filler(a, p1, p2, n_slices=n_slices, repeat=repeat)
+    r1, r2 = _bf(_ref_linear(a, w1, None)), _bf(_ref_linear(a, w2, b2))
+    assert (o1.float() - r1).abs().max().item() <= 1.5e-2 * r1.abs().max().item() + 1e-3
+    assert (o2.float() - r2).abs().max().item() <= 1.5e-2 * r2.abs().max().item() + 1e-3
+    # and exactly the whole-op result when the slices keep the K order (no rotation inside one step)
+    whole = ops.stream_gemm(a, p2, epi="bias")
+    assert (o2.float() - whole.float()).abs().max().item() <= 1.5e-2 * r2.abs().max().item() + 1e-3
+
+
+def test_head_filler_plan_cpu():
+    """The filler plan of the persistent sampler (csrc/bd_head.cu::plan_head_pieces): the pieces tile every (pass, k-block)
+    of the adaLN GEMM exactly once, in order, never span two passes, start on ring-step boundaries, and follow the slots'
+    wanted sizes — for the 14B head (4 passes x 80 k-blocks, 18 slots) and degenerate shapes."""
+    import ctypes as C
+    import __graft_entry__ as ge
+    ge.build()
+    from bitdance_b200 import _lib
+    lib = _lib.load()
+    cases = [(4, 80, [22] + [22, 8, 22] * 5 + [22, 8]), (1, 4, [22] + [22, 8, 22] * 3 + [22, 8]), (3, 5, [4, 4]),
+             (2, 12, [1] * 30), (7, 80, [22, 8] * 4), (1, 1, [5]), (4, 80, [0, 0, 10])]
+    for P, KB, want in cases:
+        out = (C.c_int * (4 * 256))()
+        n = lib.bd_head_plan_pieces(P, KB, (C.c_int * len(want))(*want), len(want), out, 256)
+        assert n > 0, (P, KB, want)
+        pcs = [tuple(out[4 * i + j] for j in range(4)) for i in range(n)]
+        pos = 0
+        for slot, p, kb0, kbn in pcs:
+            assert 0 <= slot < len(want) and kbn > 0
+            assert p * KB + kb0 == pos and kb0 + kbn <= KB, (P, KB, pcs)
+            assert kb0 % 2 == 0
+            pos += kbn
+        assert pos == P * KB
+        assert [s for s, *_ in pcs] == sorted(s for s, *_ in pcs)
+    # the path shape: sizes follow the wanted proportions within one ring step (+ the pass-end rule)
+    want = [22] + [22, 8, 22] * 5 + [22, 8]
+    out = (C.c_int * (4 * 256))()
+    n = lib.bd_head_plan_pieces(4, 80, (C.c_int * len(want))(*want), len(want), out, 256)
+    per_slot = [0] * len(want)
+    for i in range(n):
+        per_slot[out[4 * i]] += out[4 * i + 3]
+    scale = 320 / sum(want)
+    assert all(abs(g - w * scale) <= 4 for g, w in zip(per_slot, want)), per_slot
+
+
 def test_stream_host_policy_cpu():
     """host-side policy functions of the engine (no GPU): packed size and the small-N k-split rule"""
     import ctypes as C
