@@ -62,7 +62,8 @@ class BitDanceT2IPipeline:
         self.hidden_size = self.llm_config["hidden_size"]
         sd = _load_llm_state_dict(model_path)
         self.llm_model = _EmbedOnlyLLM(sd["model.embed_tokens.weight"].to(device, torch.bfloat16))
-        llm = LlmRunner(sd, self.llm_config, device=device)
+        llm = LlmRunner(sd, self.llm_config, device=device,
+                        max_positions=max(8192, int(self.llm_config.get("max_position_embeddings", 8192))))
         del sd
 
         with open(os.path.join(model_path, 'ae_config.json')) as f:

@@ -121,3 +121,74 @@ def test_tokenizer_roundtrip_vs_oracle():
     tok = q_ref.view(B, C, h // ps, ps, w // ps, ps).permute(0, 2, 4, 3, 5, 1).reshape(B, h * w, C).contiguous()
     dec2 = run.decode_tokens(tok.cuda(), h, w, ps).float().cpu()
     assert torch.equal(dec2, dec)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,bias", [
+    (1, 16, 16, 1024, 1024, 3, 1, False),   # ae_d16c32 level 4 / mid ResBlock conv (autoencoder.py:41-57)
+    (1, 16, 16, 512, 1024, 3, 1, False),    # channel-changing ResBlock conv1
+    (1, 16, 16, 512, 1024, 1, 1, False),    # its 1x1 nin_shortcut
+    (1, 16, 16, 1024, 32, 1, 1, True),      # encoder conv_out (1x1, 1024 -> z)
+    (1, 16, 16, 32, 1024, 3, 1, True),      # decoder conv_in
+    (1, 32, 32, 512, 512, 3, 2, True),      # Downsample (stride 2, bias) at 512 channels
+])
+def test_conv_baseline_channels_vs_torch(B, H, W, Cin, Cout, k, stride, bias):
+    """The channel counts the BASELINE tokenizer (ae_d16c32: ch 256 -> 1024) actually runs: 16 k-blocks per tap, 9 taps."""
+    test_conv_vs_torch(B, H, W, Cin, Cout, k, stride, bias)
+
+
+def test_conv_upsampler_1024_to_4096_depth_to_space():
+    """Upsampler of the deepest decoder level: conv 1024 -> 4096 + depth-to-space (autoencoder.py:198-249)."""
+    from bitdance_b200.ae import AERunner
+    from oracle.ae import depth_to_space
+    torch.manual_seed(5)
+    B, H, W, C = 1, 16, 16, 1024
+    w = torch.randn(4 * C, C, 3, 3) * 0.02
+    b = torch.randn(4 * C) * 0.1
+    run = AERunner({"up.weight": w, "up.bias": b}, DD_SMALL)
+    x = torch.randn(B, C, H, W)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    out = run._conv("up", xn, B, H, W, out_mode=1).float().cpu()
+    ref = depth_to_space(bf(F.conv2d(bf(x), bf(w), bf(b), padding=1))).permute(0, 2, 3, 1)
+    assert (out - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item() + 1e-3
+
+
+def test_tokenizer_ae_d16c32_256px_vs_oracle():
+    """BASELINE.json configs[0]: the real ae_d16c32 tokenizer (ch=256, ch_mult=[1,1,2,2,4], 4 ResBlocks per level,
+    460 M parameters) on one 256x256 image: encode -> sign -> pack -> decode against the CPU oracle (oracle/ae.py, bf16
+    rounding policy; ~10 s on the host). Token grid bit-exact wherever |latent| exceeds the latent error, packed bits
+    equal to the oracle's packing of the same signs, decode compared from the SAME token grid."""
+    import numpy as np
+    from bitdance_b200.synthetic import AE_D16C32
+    from oracle import ae as oa
+    from oracle import quant as oq
+    sd, run = make(AE_D16C32, seed=3, std=0.02)
+    torch.manual_seed(2)
+    x = torch.rand(1, 3, 256, 256) * 2 - 1
+    q, packed, idx, lat = run.encode(x.cuda(), num_codebooks=4)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        q_ref, lat_ref = oa.encode(sd, x, rnd=oa.bf16)
+    assert tuple(q.shape) == (1, 32, 16, 16)
+    e_lat = (lat.float().cpu() - lat_ref).abs().max().item()
+    scale = lat_ref.abs().max().item()
+    assert e_lat < 3e-2 * scale + 1e-3, f"latent err {e_lat} (scale {scale})"
+    safe = lat_ref.abs() > e_lat + 1e-3 * scale
+    assert torch.equal(q.float().cpu()[safe], q_ref[safe])
+    agree = (q.float().cpu() == q_ref).float().mean().item()
+    print(f"ae_d16c32 256px: latent err {e_lat:.4f} (scale {scale:.3f}), token agreement {agree:.4f}, "
+          f"safe fraction {safe.float().mean().item():.3f}")
+    assert agree > 0.97
+    # quantise / pack / GFQ indices of the GPU latent: bit-exact against the oracle's integer code
+    lat_np = lat.float().cpu().numpy()
+    assert np.array_equal(q.float().cpu().numpy(), oq.sign_quantize(lat_np))
+    assert np.array_equal(packed.cpu().numpy().view(np.uint32), oq.pack_bits_nchw(lat_np))
+    assert np.array_equal(idx.cpu().numpy(), oq.gfq_indices(lat_np, 4))
+    # decode from the SAME token grid
+    dec = run.decode(q_ref.cuda()).float().cpu()
+    with torch.no_grad():
+        dec_ref = oa.decoder_forward(sd, q_ref, rnd=oa.bf16)
+    e = (dec - dec_ref).abs().max().item()
+    print(f"ae_d16c32 256px: decode err {e:.4f} mean {(dec - dec_ref).abs().mean().item():.5f} "
+          f"(scale {dec_ref.abs().max().item():.2f})")
+    assert dec.shape == (1, 3, 256, 256)
+    assert e < 4e-2 * dec_ref.abs().max().item() + 2e-2, f"decode err {e}"

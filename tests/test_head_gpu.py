@@ -132,3 +132,35 @@ def test_head_full_size_properties():
     # reported, loosely bounded: with random-init weights the x-prediction is ~0, so the signs of the sample hang on rounding
     print(f"  3 steps without guidance: sign agreement {agree:.4f}, mean |diff| {(a2 - t2).abs().mean().item():.5f}")
     assert agree > 0.6
+
+
+@pytest.mark.parametrize("path", ["stream", "tiled"])
+def test_head_saturating_weights_exact_token_grid(path):
+    """SURVEY.md section 7, contract (c): with trained-like weights the x-prediction saturates to +-1 (a trained BitDance
+    head predicts bits), the SDE contracts onto those bits, and the FREE-RUNNING token grid (sign of the final sample)
+    of the GPU sampler equals the oracle's — exactly on every entry whose final |x| is not rounding-level, and here on
+    all of them. Saturation is produced by scaling the final Linear (pre-sigmoid std ~ 25), everything else is the usual
+    synthetic network; 10 sampling steps, CFG 3."""
+    from oracle import head as oh
+    cfg = dict(ch_target=32, ch_cond=256, ch_latent=256, depth_latent=4, depth_adanln=2)
+    from bitdance_b200.head import HeadRunner, head_spec
+    from bitdance_b200.synth import synth_state_dict
+    sd = synth_state_dict(head_spec(32, 256, 256, 4, 2, True), seed=1, std=0.05)
+    sd["net.final_layer.linear.weight"] = sd["net.final_layer.linear.weight"] * 30.0
+    runner = HeadRunner(sd, ch_target=32, ch_cond=256, ch_latent=256, depth_latent=4, depth_adanln=2, use_swiglu=True)
+    torch.manual_seed(0)
+    B, pn, S, guidance = 2, 16, 10, 3.0
+    z = torch.randn(2 * B, pn, 256)
+    noise = torch.randn(S + 1, B, pn, 32)
+    x, trace = runner.sample(z.cuda(), guidance, S, noise=noise.cuda(), trace=True, path=path)
+    with torch.no_grad():
+        ref = oh.euler_maruyama(sd, z, guidance, S, list(noise), rnd=oh.bf16)[:B]
+    sat = (trace[-1].abs() > 0.99).float().mean().item()
+    tok, tok_ref = torch.sign(x.cpu()), torch.sign(ref)
+    agree = (tok == tok_ref).float().mean().item()
+    safe = ref.abs() > 0.05
+    print(f"saturating head [{path}]: {sat:.3f} of the last evaluation's outputs saturated, token-grid agreement "
+          f"{agree:.5f} ({int((tok != tok_ref).sum())} of {tok.numel()} differ), safe fraction {safe.float().mean().item():.4f}")
+    assert sat > 0.9
+    assert torch.equal(tok[safe], tok_ref[safe])
+    assert agree >= 0.998

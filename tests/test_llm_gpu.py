@@ -78,3 +78,48 @@ def test_llm_split_kv_matches_unsplit():
         run.forward(x0.clone(), cache, 0, 1, causal=True, attn_splits=1)
         outs.append(run.forward(x1.clone(), cache, 0, 1, causal=False, attn_splits=splits).cpu())
     assert rel_err(outs[1], outs[0]) < 5e-3
+
+
+def test_llm_qwen3_14b_layer_vs_oracle():
+    """One decoder layer at the Qwen3-14B dimensions (hidden 5120, 40 Q / 8 KV heads x 128, MLP 17408 — the shapes the
+    bench runs 40 times per AR step): causal prefill of a 2085-token prompt (bf16 stream), the first image block
+    (block-bidirectional, bf16 stream), then an fp32-stream AR block over BOTH sequences of a CFG pair in one pass with
+    very different cache lengths (2213 vs 134 tokens: split-KV over 35 pages vs 3), against oracle/llm.py."""
+    from bitdance_b200.llm import LlmRunner, llm_spec
+    from bitdance_b200.synth import synth_state_dict
+    from bitdance_b200.synthetic import QWEN3_14B
+    from oracle import llm as ol
+    cfg = {k: v for k, v in QWEN3_14B.items() if k != "vocab_size"}
+    cfg["num_hidden_layers"] = 1
+    sd = synth_state_dict(llm_spec(cfg), seed=5, std=0.02)
+    sd = {k: v.to(torch.bfloat16).float() for k, v in sd.items()}
+    run = LlmRunner(sd, cfg, max_positions=4096)
+    torch.manual_seed(0)
+    D, pn = cfg["hidden_size"], 64
+    lens = [2085, 6]
+    cache = run.new_cache(2, lens[0] + 4 * pn)
+    ocache = [[None], [None]]
+    block0 = torch.randn(1, pn, D).to(torch.bfloat16).float()
+    with torch.no_grad():
+        for r, n in enumerate(lens):
+            prompt = torch.randn(1, n, D).to(torch.bfloat16).float()
+            run.forward(prompt.to(torch.bfloat16).cuda(), cache, r, 1, causal=True)
+            o = run.forward(block0.to(torch.bfloat16).cuda(), cache, r, 1, causal=False).float().cpu()
+            ol.decoder_forward(sd, cfg, prompt, ocache[r], causal=True, rnd=ol.bf16, stream_f32=False)
+            ref = ol.decoder_forward(sd, cfg, block0, ocache[r], causal=False, rnd=ol.bf16, stream_f32=False)
+            e = rel_err(o, ref)
+            print(f"Qwen3-14B layer, prefill + first block, seq {r} ({n} tokens): rel err {e:.4f}")
+            assert e < 3e-2
+        for step in range(2):
+            x = torch.randn(2, pn, D)
+            o = run.forward(x.clone().cuda(), cache, 0, 2, causal=False).cpu()
+            for r in range(2):
+                ref = ol.decoder_forward(sd, cfg, x[r:r + 1], ocache[r], causal=False, rnd=ol.bf16, stream_f32=True)
+                e = rel_err(o[r:r + 1], ref)
+                print(f"Qwen3-14B layer, fp32-stream AR block {step}, seq {r}: rel err {e:.4f}")
+                assert e < 3e-2
+    assert cache.seq_lens.tolist() == [lens[0] + 3 * pn, lens[1] + 3 * pn]
+    k_ref = ocache[0][0][0][0]          # [Hkv, L, hd]
+    pages = cache.page_table[0].long()
+    k_dev = cache.pool[0, 0][pages].permute(1, 0, 2, 3).reshape(cfg["num_key_value_heads"], -1, 128)[:, :k_ref.shape[1]]
+    assert rel_err(k_dev.float().cpu(), k_ref) < 2e-2
