@@ -119,6 +119,12 @@ __global__ void __launch_bounds__(256) qk_norm_rope_append_kernel(
   const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
   const int b = m / S, s = m % S;
   const int pos = seq_lens[b] + s;
+  if (pos < 0 || pos >= max_pages * 64) {
+    // the device-side sequence length ran past the cache (the CUDA-graph path has no host-side length check; the RoPE tables
+    // cover max_pages * 64 positions, llm.py::new_cache): fail loudly instead of writing K/V outside the pool
+    if (lane == 0 && hh == 0) printf("bd_llm: sequence %d position %d outside the KV cache (%d tokens)\n", b, pos, max_pages * 64);
+    __trap();
+  }
   const __nv_bfloat16* src = qkv + static_cast<long long>(m) * heads * HD + static_cast<long long>(hh) * HD + lane * VPT;
   float x[VPT];
 #pragma unroll

@@ -73,6 +73,9 @@ class T2IEngine:
         """KV pools are reused across calls (sized for the largest request so far); only the lengths are reset."""
         c = self._kv.get(R)
         if c is None or c.max_tokens < max_len:
+            # captured graphs are bound to their cache (and pin its multi-GB pool): drop them with it
+            self._graph_state = {k: v for k, v in self._graph_state.items() if v.get("R") != R}
+            c = None
             c = self.llm.new_cache(R, max_len)
             self._kv[R] = c
         c.seq_lens.zero_()
@@ -115,18 +118,18 @@ class T2IEngine:
             self.timings["prefill_s"] = time.perf_counter() - t0
             t0 = time.perf_counter()
         # ---- AR loop ----
-        tokens = torch.empty((B, h * w, self.zc), dtype=torch.float32, device=dev)
-        packed = torch.empty((B, h * w, self.zc // 32), dtype=torch.int32, device=dev)
+        tokens = torch.zeros((B, h * w, self.zc), dtype=torch.float32, device=dev)   # rows beyond a truncated loop: 0
+        packed = torch.zeros((B, h * w, self.zc // 32), dtype=torch.int32, device=dev)
         tok_bf = torch.empty((R * pn, self.zc), dtype=torch.bfloat16, device=dev)
         e1 = torch.empty((R * pn, D), dtype=torch.bfloat16, device=dev)
         splits = self.llm.plan_splits(R, pn, max_len)
         if use_graph is None:
             use_graph = self.use_graph
+        steps_done = steps
         if use_graph and steps > 2:
             self._ar_loop_graph(cache, h_fused, pos, tokens, packed, B=B, G=G, hw=h * w, steps=steps,
                                 total_steps=total_steps, guidance_scale=guidance_scale,
                                 num_sampling_steps=num_sampling_steps, splits=splits)
-            steps_done = steps
             steps = 0
         for step in range(steps):
             x = self.head.sample(h_fused, guidance_scale, num_sampling_steps)  # [B, pn, zc] fp32
@@ -144,7 +147,7 @@ class T2IEngine:
         if timers:
             torch.cuda.synchronize()
             self.timings["ar_s"] = time.perf_counter() - t0
-            self.timings["ar_steps"] = steps if steps else steps_done
+            self.timings["ar_steps"] = steps_done
         return tokens, packed
 
     # ---- CUDA-graph AR loop ------------------------------------------------------------------------------------------
@@ -166,6 +169,13 @@ class T2IEngine:
                                out_add_mod=pn, attn_splits=splits, sk_bound=cache.max_tokens, track_host=False)
         st["h_fused"].copy_(out)
 
+    def _scratch_ptrs(self):
+        """Addresses of every grow-only scratch buffer a captured AR step bakes in (they live outside the graph pool)."""
+        llm_ws = self.llm._ws.data_ptr() if self.llm._ws is not None else 0
+        head_ws = tuple(sorted((k, v.data_ptr()) for k, v in self.head._ws.items()))
+        gemm_ws = ops.default_workspace(self.device).buf
+        return (llm_ws, head_ws, gemm_ws.data_ptr() if gemm_ws is not None else 0)
+
     def _ar_loop_graph(self, cache, h_fused, pos, tokens, packed, *, B, G, hw, steps, total_steps, guidance_scale,
                        num_sampling_steps, splits):
         """Capture ONE AR step (head sampler + sign + projector + LLM block: ~3 500 kernel launches with their
@@ -176,7 +186,7 @@ class T2IEngine:
         key = (B, G, guidance_scale, num_sampling_steps, splits, cache.max_tokens)
         st = self._graph_state.get(key)
         if st is None:
-            st = dict(B=B, G=G,
+            st = dict(B=B, G=G, R=R,
                       h_fused=torch.empty((R, pn, D), dtype=torch.float32, device=dev),
                       pos_cur=torch.empty((pn, D), dtype=torch.float32, device=dev),
                       pos_next=torch.empty((pn, D), dtype=torch.float32, device=dev),
@@ -198,6 +208,10 @@ class T2IEngine:
             packed[:, step * pn:(step + 1) * pn].copy_(st["packed_stage"])
 
         first = 0
+        if st["graph"] is not None and st.get("ws_ptrs") != self._scratch_ptrs():
+            # a grow-only scratch buffer (LLM / head / GEMM workspace) was re-allocated since the capture — e.g. by a
+            # prefill with a longer prompt: the graph holds the freed address. Capture again.
+            st["graph"] = None
         if st["graph"] is None or st["cache_id"] != id(cache.pool):
             # the graph bakes in the KV pool / page-table / seq_lens addresses of this cache: keep the cache with the graph
             stage(0)
@@ -211,6 +225,7 @@ class T2IEngine:
                 self._ar_step_body(st, cache, guidance_scale, num_sampling_steps, splits)
             # capture does not execute: seq_lens was not bumped, h_fused not advanced -> replay step 1 for real
             st["graph"], st["cache_id"], st["cache"] = g, id(cache.pool), cache
+            st["ws_ptrs"] = self._scratch_ptrs()
         else:
             # re-use the captured graph: it is bound to its own cache object -> copy the prefilled state into it
             gc = st["cache"]

@@ -1,0 +1,23 @@
+#!/bin/bash
+# One GPU lease: tests, timelines and micro-benchmarks, each under its own timeout; logs land in gpurun_out/.
+set +e
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+TAG=${TAG:-r02}
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
+nproc >> gpurun_out/${TAG}_gpu.txt
+for step in "$@"; do
+  case "$step" in
+    stream)   timeout 600 python -m pytest tests/test_stream_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/${TAG}_test_stream.log ;;
+    head)     timeout 900 python -m pytest tests/test_head_gpu.py -m gpu -q -s 2>&1 | tail -60 > gpurun_out/${TAG}_test_head.log ;;
+    tests)    timeout 2400 python -m pytest tests -m gpu -q -s 2>&1 | tail -150 > gpurun_out/${TAG}_tests.log ;;
+    timeline) timeout 900 python scripts/head_timeline.py > gpurun_out/${TAG}_head_timeline.txt 2>&1 ;;
+    ae)       timeout 900 python scripts/ae_bench.py > gpurun_out/${TAG}_ae_bench.txt 2>&1 ;;
+    bench)    timeout 1500 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
+    benchref) timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err ;;
+    smoke)    timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1 ;;
+    *) echo "unknown step $step" ;;
+  esac
+  echo "$step rc=$?" >> gpurun_out/${TAG}_steps.log
+done
+tail -5 gpurun_out/${TAG}_*.log 2>/dev/null | tail -60
