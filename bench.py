@@ -84,82 +84,64 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port) on the host cores, bounded sample, extrapolated
+# Reference arms: the UNMODIFIED reference (oracle/_ref, shipped by oracle/make_ref.py) on the host cores / on the GPU
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(S: int, threads: int):
-    """Times, at the 14B-64x dimensions (M = 128 rows), ONE diffusion-head evaluation (all 6 blocks sharing one
-    block's random weights to bound RAM) and ONE Qwen3 decoder layer over a 2100-token cache, fp32 math via the oracle
-    port (oracle/head.py, oracle/llm.py), then extrapolates an image: 64 x (51 head evals + 40 layers) (prefill and
-    tokenizer decode excluded: < 2 % of the work). Returns (images_per_sec, seconds_measured, description)."""
+AR_STEPS_PER_IMAGE = {"BitDance-14B-64x": 64, "BitDance-14B-16x": 256}
+
+
+def reference_sample(model: str, device: str, n_warm: int, n_timed: int, S: int, guidance: float, height: int, bs: int,
+                     threads: int | None = None, with_decode: bool = True):
+    """Times the reference's own ``BitDanceT2IPipeline.gen_image`` (oracle/ref_runner.py: its classes, its loop, random-init
+    weights of the named architecture, bf16 autocast as in ``generate()``) on a BOUNDED sample: the causal prefill of the
+    cond + uncond prompts, then ``n_warm + n_timed`` AR steps of the unmodified loop (each = 51-evaluation DiffHead.sample
+    + sign + MLPconnector + two Qwen3-14B passes over the growing KV cache), then the tokenizer decode of one grid. The
+    image time is extrapolated: prefill + (AR steps per image) x median timed step + decode. The sampled steps are the
+    FIRST ones of an image (KV cache of ~130-600 tokens against ~2 100 on average): the attention share is underestimated,
+    i.e. the extrapolation favours the reference."""
+    import statistics
     import torch
-    from oracle import head as oh, llm as ol
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    D, hid, C, pn, R = 5120, 7680, 32, 64, 2
-
-    def lin(o, i):
-        return torch.randn(o, i) * 0.02, torch.zeros(o)
-
-    sd = {}
-    for name, (o, i) in {"net.time_embed.mlp.0": (D, 256), "net.time_embed.mlp.2": (D, D), "net.cond_embed": (D, D),
-                         "net.input_proj": (D, C), "net.final_layer.ada_ln_modulation": (2 * D, D),
-                         "net.final_layer.linear": (C, D)}.items():
-        sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
-    blk = {"attn.wqkv": (3 * D, D), "attn.wo": (D, D), "w1": (2 * hid, D), "w2": (D, hid)}
-    shared = {k: lin(*v) for k, v in blk.items()}
-    ada = lin(6 * D, D)
-    for b in range(6):
-        for k, (w, bias) in shared.items():
-            sd[f"net.res_blocks.{b}.{k}.weight"], sd[f"net.res_blocks.{b}.{k}.bias"] = w, bias
-        for n in ("norm1", "norm2"):
-            sd[f"net.res_blocks.{b}.{n}.weight"], sd[f"net.res_blocks.{b}.{n}.bias"] = torch.ones(D), torch.zeros(D)
-    for a in range(2):
-        sd[f"net.ada_ln_blocks.{a}.weight"], sd[f"net.ada_ln_blocks.{a}.bias"] = ada
-    x, t, c = torch.randn(R, pn, C), torch.full((R,), 0.3), torch.randn(R, pn, D)
-    cfg = dict(num_attention_heads=40, num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6,
-               num_hidden_layers=1)
-    sdl = {"model.layers.0.input_layernorm.weight": torch.ones(D), "model.layers.0.post_attention_layernorm.weight": torch.ones(D),
-           "model.layers.0.self_attn.q_norm.weight": torch.ones(128), "model.layers.0.self_attn.k_norm.weight": torch.ones(128),
-           "model.norm.weight": torch.ones(D)}
-    for n, (o, i) in {"self_attn.q_proj": (5120, D), "self_attn.k_proj": (1024, D), "self_attn.v_proj": (1024, D),
-                      "self_attn.o_proj": (D, 5120), "mlp.gate_proj": (17408, D), "mlp.up_proj": (17408, D),
-                      "mlp.down_proj": (D, 17408)}.items():
-        sdl[f"model.layers.0.{n}.weight"] = torch.randn(o, i) * 0.02
-    ctx = 2100
-    with torch.no_grad():
-        oh.head_forward(sd, x, t, c)  # warm-up (thread pool, allocator)
-        t0 = time.perf_counter()
-        oh.head_forward(sd, x, t, c)
-        t_head = time.perf_counter() - t0
-        cache = [[torch.randn(R, 8, ctx, 128), torch.randn(R, 8, ctx, 128)]]
-        xin = torch.randn(R, pn, D)
-        t0 = time.perf_counter()
-        ol.decoder_forward(sdl, cfg, xin, cache, causal=False)
-        t_layer = time.perf_counter() - t0
-    sec_per_image = 64 * ((S + 1) * t_head + 40 * t_layer)
-    desc = (f"oracle port fp32, {threads} threads: 1 head evaluation ({t_head:.2f} s, M=128, 1.76 B params) + 1 Qwen3-14B "
-            f"layer over a {ctx}-token cache ({t_layer:.2f} s), extrapolated to 64 x ({S + 1} evals + 40 layers)")
-    return 1.0 / sec_per_image, t_head + t_layer, desc
+    from oracle import ref_runner as rr
+    if device == "cpu" and threads:
+        torch.set_num_threads(threads)
+    pipe, info = rr.build_pipeline(model, device, with_ae=with_decode)
+    run = rr.run_bounded(pipe, info, n_ar=n_warm + n_timed, image_px=height, guidance=guidance, S=S, num_images=bs)
+    timed = run["ar_s"][n_warm:]
+    ar = statistics.median(timed)
+    dec = rr.time_decode(pipe, image_px=height, num_images=bs) if with_decode else 0.0
+    steps = AR_STEPS_PER_IMAGE.get(model, 64)
+    sec_per_batch = run["prefill_s"] + steps * ar + dec
+    desc = (f"unmodified reference gen_image on {device} ({'all ' + str(threads) + ' host threads, ' if device == 'cpu' else ''}"
+            f"bf16 autocast, random-init {model}): prefill {run['prefill_s']:.2f} s + {n_warm} warm-up + {n_timed} timed AR steps "
+            f"(median {ar:.3f} s, all {[round(x, 3) for x in run['ar_s']]}) + decode {dec:.2f} s; image = prefill + {steps} x "
+            f"median + decode (extrapolated)")
+    out = dict(images_per_s=bs / sec_per_batch, ar_step_s=ar, prefill_s=run["prefill_s"], decode_s=dec, build_s=info["build_s"],
+               sample=desc, measured_s=run["total_s"] + dec)
+    del pipe, info
+    return out
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vals = []
-    desc = ""
-    for i in range(args.warmup + args.steps):
-        v, secs, desc = cpu_reference_sample(args.sampling_steps, threads)
-        if i >= args.warmup:
-            vals.append(v)
-    value = sum(vals) / len(vals)
+    B, S = args.bs, args.sampling_steps
+    try:
+        r = reference_sample(args.model, "cpu", args.warmup, args.steps, S, args.guidance, args.height, B, threads)
+    except Exception as e:  # the shipped copy is missing (oracle/make_ref.py not run) or the host cannot hold the model
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"[:300]}))
+        return
+    value = r["images_per_s"]
+    steps = AR_STEPS_PER_IMAGE.get(args.model, 64)
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{MODEL} random-init, 1024x1024, 64 AR steps, bs=1, CFG 7.5, S={args.sampling_steps}",
-                       "extrapolated": True},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": desc},
+            "warmup": args.warmup, "ms_per_step": 1000.0 * B / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.model} random-init, {args.height}x{args.width}, {steps} AR steps, bs={B}, "
+                                   f"CFG {args.guidance}, S={S} (+1), synthetic 64-token prompt",
+                       "extrapolated": True, "step": "one AR step of the unmodified loop", "ms_per_ar_step": 1e3 * r["ar_step_s"],
+                       "prefill_ms": 1e3 * r["prefill_s"], "decode_ms": 1e3 * r["decode_s"]},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "reference", "sample": r["sample"]},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -181,6 +163,7 @@ def main():
     ap.add_argument("--guidance", type=float, default=7.5)
     ap.add_argument("--ar-steps", type=int, default=None, help="debug only: truncate the AR loop (invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the GPU-eager reference leg")
     ap.add_argument("--no-roofline", action="store_true", help="profiling runs: skip the live dominant-kernel timing")
     ap.add_argument("--graph", type=int, default=1, help="replay the AR step as a CUDA graph (1) or launch it eagerly (0)")
     args = ap.parse_args()
@@ -231,15 +214,22 @@ def main():
             return None
         return eng.decode(tokens, h, w)
 
+    # ---- the PUBLIC call: BitDanceT2IPipeline.generate(prompt, ...) -> list[PIL.Image] (t2i_pipeline.py:110-155) over the
+    # same engine: host tokenizer, embedding lookup, token ids H2D, the whole path, uint8 pixels D2H, PIL conversion
+    from bitdance_b200.modeling.t2i_pipeline import BitDanceT2IPipeline
+    from bitdance_b200.synthetic import synthetic_tokenizer
+    tokenizer, prompt = synthetic_tokenizer(m["llm"]["vocab_size"], pn, n_words=59)
+    pipe = BitDanceT2IPipeline.from_engine(eng, tokenizer=tokenizer, embed_weight=embed, device=dev)
+    n_prompt = len(tokenizer.encode(f"<|im_start|>user\n{prompt}<|im_end|>\n<|im_start|>assistant\n"))
+    n_uncond = len(tokenizer.encode("<|im_start|>assistant\n"))
+    e2e_h2d = 8 * (n_prompt + n_uncond + 2 + pn)
+
     def gen_e2e():
-        """The public call with HOST buffers: token ids H2D, uint8 pixels D2H (generate(), t2i_pipeline.py:110-155)."""
-        ids_dev = ids_host.to(dev, non_blocking=True)
-        img = gen_resident(ids_dev)
-        if img is None:
-            return
-        u8 = torch.clamp(127.5 * img + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)
-        img_host.copy_(u8, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if args.ar_steps is not None:
+            return gen_resident(ids_host.to(dev, non_blocking=True))
+        imgs = pipe.generate(prompt, height=args.height, width=args.width, num_sampling_steps=S,
+                             guidance_scale=args.guidance, num_images=B, seed=1234 + rank)
+        assert len(imgs) == B and imgs[0].size == (args.width, args.height)
 
     ids_dev = ids_host.to(dev)
 
@@ -313,14 +303,36 @@ def main():
                    "cuda_graph": bool(args.graph), "ms_per_ar_step": ms_ar, "prefill_ms": 1e3 * phases.get("prefill_s", 0.0),
                    "truncated_ar_steps": args.ar_steps},
         "clocks": clk.summary(),
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(ids_host.numel() * 8),
-                "d2h_bytes_per_step": int(img_host.numel())},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(e2e_h2d),
+                "d2h_bytes_per_step": int(img_host.numel()),
+                "call": f"BitDanceT2IPipeline.generate(prompt[{n_prompt} tokens], {args.height}, {args.width}, {S}, "
+                        f"{args.guidance}, num_images={B}) -> list[PIL.Image]: host tokenizer + embedding lookup + ids H2D + "
+                        f"prefill + AR loop + decode + uint8 D2H + PIL"},
         "gpu_launches": int(launches),
         "roofline": roof,
     }
+    if not args.no_gpu_reference and world == 1:
+        # SURVEY.md section 8d's "number to beat": the unmodified reference, eager PyTorch on this same B200 under CUDA
+        # autocast (bounded: prefill + 1 warm-up + 3 timed AR steps, extrapolated like the CPU arm)
+        try:
+            del pipe
+            torch.cuda.empty_cache()
+            g = reference_sample(args.model, f"cuda:{local}", 1, 3, S, args.guidance, args.height, B)
+            line["gpu_eager_reference"] = {"value": g["images_per_s"], "unit": "images/s", "ms_per_ar_step": 1e3 * g["ar_step_s"],
+                                           "prefill_ms": 1e3 * g["prefill_s"], "decode_ms": 1e3 * g["decode_s"],
+                                           "speedup_e2e": e2e_value / g["images_per_s"], "sample": g["sample"]}
+            torch.cuda.empty_cache()
+        except Exception as e:
+            line["gpu_eager_reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     if not args.no_cpu_baseline:
-        v, secs, desc = cpu_reference_sample(S, os.cpu_count() or 1)
-        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
+        try:
+            threads = os.cpu_count() or 1
+            r = reference_sample(args.model, "cpu", 1, 1, S, args.guidance, args.height, B, threads, with_decode=False)
+            line["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": threads, "kind": "reference",
+                                    "sample": r["sample"] + " [decode not timed in this leg]"}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                    "sample": f"unavailable: {type(e).__name__}: {e}"[:300]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libbitdance_b200.so")
+# BD_LIB_PATH: measurement only (A/B of two builds of the library on the same box, scripts/head_ab.py)
+LIB_PATH = os.environ.get("BD_LIB_PATH") or os.path.join(_HERE, "_C", "libbitdance_b200.so")
 
 
 class BitDanceNativeError(RuntimeError):

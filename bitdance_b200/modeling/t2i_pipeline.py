@@ -107,6 +107,23 @@ class BitDanceT2IPipeline:
         self._finish(llm)
         return self
 
+    @classmethod
+    def from_engine(cls, engine: T2IEngine, *, tokenizer, embed_weight, device='cuda'):
+        """The public surface over an already-built engine (bench.py: synthetic 14B weights generated on the device, so
+        there are no nn.Module copies of them): ``generate`` / ``gen_image`` / ``decode_image`` work as usual; ``ae`` /
+        ``vision_head`` / ``embed_vision_mlp`` expose only their native runners."""
+        self = object.__new__(cls)
+        self.device, self.tokenizer, self.engine = device, tokenizer, engine
+        self.hidden_size = engine.D
+        self.llm_config = dict(engine.llm.cfg)
+        self.llm_model = _EmbedOnlyLLM(embed_weight.to(device, torch.bfloat16))
+        self.ae = types.SimpleNamespace(runner=engine.ae)
+        self.vision_head = types.SimpleNamespace(runner=engine.head)
+        self.embed_vision_mlp = None
+        self.vae_patch_size, self.parallel_num, self.ps = engine.vae_patch_size, engine.pn, engine.ps
+        self.pos_embed_1d = engine.pos_1d
+        return self
+
     def _finish(self, llm: LlmRunner):
         p = self.embed_vision_mlp
         self.engine = T2IEngine(llm, self.vision_head.runner, self.ae.runner, p.fc1.weight, p.fc1.bias, p.fc2.weight,

@@ -99,3 +99,29 @@ def engine_from_state_dicts(sds: dict, model: str = "tiny", device="cuda", paral
     p = sds["proj"]
     return T2IEngine(llm, head, ae, p["fc1.weight"], p["fc1.bias"], p["fc2.weight"], p["fc2.bias"],
                      parallel_num=parallel_num or m["parallel_num"], vae_patch_size=vps, device=device, pe_max_len=1024)
+
+
+def special_tokens(pn: int, max_res: int = 160):
+    """The added tokens the pipeline looks up (t2i_pipeline.py:182-192): chat markers, <|vision_start|>, <|res_N|>, <|query_i|>."""
+    return (["<|im_start|>", "<|im_end|>", "<|vision_start|>", "<|vision_end|>"]
+            + [f"<|res_{i}|>" for i in range(1, max_res + 1)] + [f"<|query_{i}|>" for i in range(1, pn)])
+
+
+def synthetic_tokenizer(vocab_size: int, pn: int, n_words: int = 56, save_to: str | None = None):
+    """An offline stand-in for the Qwen tokenizer files (no network): a word-level ``tokenizers`` model wrapped in
+    ``PreTrainedTokenizerFast`` with the special tokens above. Returns (tokenizer, a prompt of ``n_words`` words)."""
+    from tokenizers import Regex, Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+    words = ["user", "assistant", "a", "photo", "of", "cat", "dog", "red", "blue", "the", "on", "table", "\n", "[UNK]"]
+    words += [f"w{i}" for i in range(64)]
+    sp = special_tokens(pn)
+    assert len(words) + len(sp) <= vocab_size
+    tok = Tokenizer(models.WordLevel(vocab={w: i for i, w in enumerate(words)}, unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.Sequence([pre_tokenizers.Split(Regex(r"\n"), behavior="isolated"),
+                                                 pre_tokenizers.WhitespaceSplit()])
+    fast = PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="[UNK]")
+    fast.add_special_tokens({"additional_special_tokens": sp})
+    if save_to is not None:
+        fast.save_pretrained(save_to)
+    prompt = " ".join((["a", "photo", "of", "the", "red", "cat", "on", "table"] + [f"w{i}" for i in range(64)])[:n_words])
+    return fast, prompt

@@ -1,5 +1,7 @@
-"""Import the UNMODIFIED reference from /root/reference (dev container only) with the three oracle-side shims of
-SURVEY.md §8c. TEST INFRASTRUCTURE ONLY. Used to pin the oracle restatements and to generate tests/golden/*.
+"""Import the UNMODIFIED reference — from /root/reference in the dev container, else from the verbatim copy
+``oracle/make_ref.py`` ships to the GPU box under ``oracle/_ref/reference`` (git-ignored) — with the three oracle-side
+shims of SURVEY.md §8c. TEST / BASELINE INFRASTRUCTURE ONLY: pins the oracle restatements, generates tests/golden/*, and
+is what ``bench.py --impl reference`` times.
 
 Shims (none alters arithmetic):
   A  flash_attn_func -> eager softmax attention in [B,S,H,D] layout (flash_attn has no CPU backend)
@@ -13,7 +15,8 @@ import sys
 
 import torch
 
-REF = "/root/reference"
+_SHIPPED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")
+REF = "/root/reference" if os.path.isdir("/root/reference/modeling") else _SHIPPED
 
 
 def available() -> bool:
@@ -38,12 +41,15 @@ def import_reference():
     on sys.path and then moved out of ``sys.modules`` (the namespace keeps the module objects alive)."""
     global _done, _ns
     if not available():
-        raise RuntimeError("/root/reference not present")
+        raise RuntimeError("reference not present (neither /root/reference nor oracle/_ref/reference: run oracle/make_ref.py "
+                           "in the dev container)")
     if _ns is not None:
         return _ns
     import types
 
     try:
+        if not torch.cuda.is_available():
+            raise ImportError("flash_attn has no CPU backend")
         import flash_attn  # noqa: F401
     except Exception:
         m = types.ModuleType("flash_attn")
@@ -75,7 +81,8 @@ def import_reference():
     if REF not in sys.path:
         sys.path.append(REF)  # the reference's own `utils.fs` etc. stay importable, behind this repo's packages
 
-    fh.flash_attn_func = _eager_flash
+    if not torch.cuda.is_available():
+        fh.flash_attn_func = _eager_flash  # shim A (CPU); on a GPU the reference keeps the real flash_attn kernel
     from transformers import DynamicCache
     from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
 

@@ -1,0 +1,192 @@
+"""Run the UNMODIFIED reference pipeline (``BitDanceT2IPipeline.gen_image``, modeling/t2i_pipeline.py:158-272) at a named
+model configuration with random-init weights, on the host cores or on the GPU. BASELINE INFRASTRUCTURE ONLY
+(``bench.py --impl reference``, bench.py's ``gpu_eager_reference`` leg, tests): the product never imports this.
+
+What is the reference's and what is the harness's:
+  * reference, untouched: gen_image's body (prompt embedding, causal prefill + block-bidirectional first block for the
+    cond and uncond prompts, the AR loop: vision_head.sample -> sign -> embed_vision_mlp -> + pos-embed -> two
+    Qwen3Model passes), DiffHead / TransEncoder / euler_maruyama, MLPconnector, VQModel, the transformers Qwen3 model;
+  * harness: the object is assembled with ``object.__new__`` (no checkpoint files exist offline; the constructor only
+    loads files), a stub tokenizer returns fixed ids, weights are N(0, 0.02) (norm scales 1), the three shims of
+    SURVEY.md section 8c (``oracle/ref_harness.py``), and — to BOUND the run — ``max_length`` is set to ``n_ar * parallel_num``
+    so that the unmodified loop runs ``n_ar`` AR steps, with ``decode_image`` replaced by a no-op for that call (the
+    tokenizer decode is timed separately). Per-step wall times come from the loop's own progress hook (``tqdm``'s
+    ``update``), nothing inside the loop is touched.
+  * precision: the reference runs under ``torch.autocast(device_type, bfloat16)`` with a bf16 LLM and fp32
+    head / projector / tokenizer weights — exactly what ``generate()`` sets up on CUDA (t2i_pipeline.py:130); on CPU the
+    same policy through CPU autocast (the hard-coded ``autocast("cuda")`` is a no-op there).
+"""
+from __future__ import annotations
+
+import time
+import types
+
+import torch
+
+from . import ref_harness as rh
+
+QWEN3_14B = dict(hidden_size=5120, intermediate_size=17408, num_hidden_layers=40, num_attention_heads=40,
+                 num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6, vocab_size=151936)
+AE_D16C32 = dict(double_z=False, z_channels=32, in_channels=3, out_ch=3, ch=256, ch_mult=[1, 1, 2, 2, 4], num_res_blocks=4)
+CONFIGS = {
+    "BitDance-14B-64x": dict(llm=QWEN3_14B, ae=AE_D16C32, parallel_num=64,
+                             head=dict(ch_target=32, ch_cond=5120, ch_latent=5120, depth_latent=6, depth_adanln=2,
+                                       use_swiglu=True)),
+    "BitDance-14B-16x": dict(llm=QWEN3_14B, ae=AE_D16C32, parallel_num=16,
+                             head=dict(ch_target=32, ch_cond=5120, ch_latent=5120, depth_latent=6, depth_adanln=2,
+                                       use_swiglu=True)),
+    "tiny": dict(llm=dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                          num_key_value_heads=2, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6, vocab_size=512),
+                 ae=dict(double_z=False, z_channels=32, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2], num_res_blocks=1),
+                 parallel_num=16,
+                 head=dict(ch_target=32, ch_cond=256, ch_latent=256, depth_latent=2, depth_adanln=2, use_swiglu=True)),
+}
+
+
+class StubTokenizer:
+    """Fixed synthetic prompt: 64 cond ids, 3 uncond ids, fixed special ids."""
+
+    def __init__(self, vocab: int, n_cond: int = 64, n_uncond: int = 3, seed: int = 1):
+        g = torch.Generator().manual_seed(seed)
+        hi = max(8, min(vocab - 300, 151000))
+        self.cond = torch.randint(0, hi, (n_cond,), generator=g).tolist()
+        self.uncond = torch.randint(0, hi, (n_uncond,), generator=g).tolist()
+        self.base = vocab - 280
+
+    def encode(self, s):
+        return self.cond if s == "cond" else self.uncond
+
+    def convert_tokens_to_ids(self, tk):
+        if tk == "<|vision_start|>":
+            return self.base
+        if tk.startswith("<|res_"):
+            return self.base + 1 + int(tk[6:-2]) % 100
+        return self.base + 110 + int(tk[8:-2])
+
+
+def _randomize(module, seed: int, std: float = 0.02):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.dim() == 1 and ("norm" in name or name.endswith("gn.weight")) and name.endswith("weight"):
+                p.fill_(1.0)
+            elif p.dim() == 1:
+                p.zero_()
+            elif p.device.type == "cpu":
+                p.copy_((torch.randn(p.shape, generator=g, dtype=torch.float32) * std).to(p.dtype))
+            else:
+                p.normal_(0.0, std)
+
+
+def build_pipeline(model: str = "BitDance-14B-64x", device: str = "cpu", seed: int = 0, with_ae: bool = True):
+    """-> (pipe, info). The reference's own classes with random-init weights (bf16 LLM; fp32 head / projector / AE)."""
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    from transformers.initialization import no_init_weights
+    ref = rh.import_reference()
+    m = CONFIGS[model]
+    t0 = time.perf_counter()
+    lc = dict(m["llm"])
+    cfg = Qwen3Config(max_position_embeddings=8192, tie_word_embeddings=False, **lc)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with no_init_weights(), torch.device(device):
+            hf = Qwen3ForCausalLM(cfg).eval()   # parameters allocated uninitialised in bf16 on `device`; buffers computed
+    finally:
+        torch.set_default_dtype(old)
+    with torch.no_grad():
+        for name, p in hf.named_parameters():
+            if p.dim() == 1:
+                p.fill_(1.0)
+            else:
+                p.normal_(0.0, 0.02)
+    with torch.device(device):
+        head = ref.fh.DiffHead(parallel_num=m["parallel_num"], **m["head"]).eval()
+        proj = ref.mu.MLPconnector(m["ae"]["z_channels"], lc["hidden_size"], "gelu_pytorch_tanh").eval()
+        ae = ref.ae.VQModel(m["ae"]).eval() if with_ae else None
+    _randomize(head, seed + 2)   # incl. the tensors the reference zero-initialises
+    _randomize(proj, seed + 4)
+    if ae is not None:
+        _randomize(ae, seed + 3)
+    P = ref.t2i.BitDanceT2IPipeline
+    pipe = object.__new__(P)
+    pipe.device, pipe.tokenizer, pipe.llm_model = device, StubTokenizer(lc["vocab_size"]), hf
+    pipe.hidden_size, pipe.ae, pipe.vision_head, pipe.embed_vision_mlp = lc["hidden_size"], ae, head, proj
+    pipe.vae_patch_size = 2 ** (len(m["ae"]["ch_mult"]) - 1)
+    pipe.parallel_num = m["parallel_num"]
+    pipe.ps = int(m["parallel_num"] ** 0.5)
+    pipe.build_pos_embed()
+    if hasattr(pipe, "pos_embed_1d") and isinstance(pipe.pos_embed_1d, torch.Tensor):
+        pipe.pos_embed_1d = pipe.pos_embed_1d.to(device)
+    return pipe, dict(model=model, ref=ref, build_s=time.perf_counter() - t0,
+                      params=sum(p.numel() for p in hf.parameters()) + sum(p.numel() for p in head.parameters()))
+
+
+class _StepClock:
+    """Stands in for ``tqdm`` inside the reference module: records a timestamp at every ``update`` (= top of every AR
+    step); the GPU arm synchronises first so that the stamps are device-complete times."""
+
+    def __init__(self, sync):
+        self.sync = sync
+        self.stamps = []
+
+    def __call__(self, *a, **k):
+        return self
+
+    def update(self, n=1):
+        if self.sync:
+            torch.cuda.synchronize()
+        self.stamps.append(time.perf_counter())
+
+
+def run_bounded(pipe, info, *, n_ar: int, image_px: int = 1024, guidance: float = 7.5, S: int = 50, num_images: int = 1,
+                seed: int = 1234):
+    """One call of the UNMODIFIED gen_image bounded to ``n_ar`` AR steps. Returns dict(prefill_s, ar_s=[...], total_s)."""
+    ref = info["ref"]
+    dev = pipe.device
+    is_cuda = str(dev).startswith("cuda")
+    clock = _StepClock(is_cuda)
+    old_tqdm, old_decode = ref.t2i.tqdm, pipe.__dict__.get("decode_image")
+    ref.t2i.tqdm = clock
+    pipe.decode_image = types.MethodType(lambda self, *a, **k: None, pipe)
+    torch.manual_seed(seed)
+    try:
+        with torch.no_grad(), torch.autocast("cuda" if is_cuda else "cpu", dtype=torch.bfloat16):
+            if is_cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pipe.gen_image("cond", "uncond", guidance_scale=guidance, num_sampling_steps=S,
+                           max_length=n_ar * pipe.parallel_num, num_images=num_images, image_size=[image_px, image_px],
+                           show_progress=True)
+            if is_cuda:
+                torch.cuda.synchronize()
+            t1 = time.perf_counter()
+    finally:
+        ref.t2i.tqdm = old_tqdm
+        if old_decode is None:
+            del pipe.__dict__["decode_image"]
+        else:
+            pipe.decode_image = old_decode
+    st = clock.stamps + [t1]
+    return dict(prefill_s=st[0] - t0, ar_s=[st[i + 1] - st[i] for i in range(len(st) - 1)], total_s=t1 - t0)
+
+
+def time_decode(pipe, *, image_px: int = 1024, num_images: int = 1, reps: int = 1):
+    """The tokenizer decode of one random token grid through the reference's own decode_image."""
+    dev = pipe.device
+    is_cuda = str(dev).startswith("cuda")
+    h = image_px // pipe.vae_patch_size
+    tok = torch.sign(torch.randn(num_images, h * h, pipe.ae.encoder.conv_out.out_channels if hasattr(pipe.ae.encoder, "conv_out") else 32,
+                                 device=dev))
+    best = None
+    with torch.no_grad(), torch.autocast("cuda" if is_cuda else "cpu", dtype=torch.bfloat16):
+        for _ in range(reps):
+            if is_cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pipe.decode_image(tok, [h, h], ps=pipe.ps)
+            if is_cuda:
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best

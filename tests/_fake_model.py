@@ -11,24 +11,9 @@ import os
 import torch
 
 
-def special_tokens(pn: int, max_res: int = 160):
-    return (["<|im_start|>", "<|im_end|>", "<|vision_start|>", "<|vision_end|>"]
-            + [f"<|res_{i}|>" for i in range(1, max_res + 1)] + [f"<|query_{i}|>" for i in range(1, pn)])
-
-
 def write_tokenizer(path: str, vocab_size: int, pn: int):
-    from tokenizers import Regex, Tokenizer, models, pre_tokenizers
-    from transformers import PreTrainedTokenizerFast
-    words = ["user", "assistant", "a", "photo", "of", "cat", "dog", "red", "blue", "the", "on", "table", "\n", "[UNK]"]
-    sp = special_tokens(pn)
-    assert len(words) + len(sp) <= vocab_size
-    vocab = {w: i for i, w in enumerate(words)}
-    tok = Tokenizer(models.WordLevel(vocab=vocab, unk_token="[UNK]"))
-    tok.pre_tokenizer = pre_tokenizers.Split(Regex(r"\n|[^\s]+"), behavior="isolated")
-    fast = PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="[UNK]")
-    fast.add_special_tokens({"additional_special_tokens": sp})
-    assert len(fast) <= vocab_size
-    fast.save_pretrained(path)
+    from bitdance_b200.synthetic import synthetic_tokenizer
+    synthetic_tokenizer(vocab_size, pn, save_to=path)
 
 
 def write_model_dir(path: str, seed: int = 0) -> dict:

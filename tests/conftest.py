@@ -10,16 +10,18 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
-    config.addinivalue_line("markers", "reference: needs /root/reference (dev container only)")
+    config.addinivalue_line("markers", "reference: needs the unmodified reference (/root/reference, or the copy "
+                                               "oracle/make_ref.py ships under oracle/_ref)")
 
 
 def pytest_collection_modifyitems(config, items):
     import torch
 
     has_gpu = torch.cuda.is_available()
-    has_ref = os.path.isdir("/root/reference/modeling")
+    has_ref = (os.path.isdir("/root/reference/modeling")
+               or os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "reference", "modeling")))
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
-    skip_ref = pytest.mark.skip(reason="/root/reference not present")
+    skip_ref = pytest.mark.skip(reason="reference not present (run oracle/make_ref.py in the dev container)")
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(skip_gpu)

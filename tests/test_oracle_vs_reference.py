@@ -40,7 +40,8 @@ def _capture_noise(fn):
 
 def test_quantiser_and_gfq_vs_reference(ref):
     import sys
-    sys.path.insert(0, "/root/reference/imagenet_gen")
+    from oracle import ref_harness as _rh
+    sys.path.insert(0, _rh.REF + "/imagenet_gen")
     from src.gfq import GFQ
     from oracle import quant as oq
     torch.manual_seed(0)
@@ -201,7 +202,8 @@ def test_imagenet_sample_vs_reference():
     import sys
     import torch.nn as nn
     import torch._dynamo
-    sys.path.insert(0, "/root/reference/imagenet_gen")
+    from oracle import ref_harness as _rh
+    sys.path.insert(0, _rh.REF + "/imagenet_gen")
     old_disable = torch._dynamo.config.disable
     torch._dynamo.config.disable = True
     try:
