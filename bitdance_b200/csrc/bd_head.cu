@@ -9,6 +9,7 @@
 //   * the 2 adaLN Linears and final_layer.ada_ln_modulation share their input y: one GEMM over concatenated weights;
 //   * the rows of cat([x, x]) (cond | uncond halves, sampling_x.py:71) are written once and duplicated.
 // Noise is an input (drawn by torch in the reference's call order), so the sampler itself is deterministic.
+#include <cstdlib>
 #include "bd_host.h"
 #include "bd_ptx.cuh"
 #include "bd_rowops.cuh"
@@ -341,7 +342,11 @@ static size_t blocked_bytes(int K) { return static_cast<size_t>((K + 63) / 64) *
 
 // Filler policy (bd_head_set_fillers): 0 = the adaLN GEMM runs in line at the start of every evaluation (round-1 program);
 // 1 = the adaLN GEMM of evaluation i + 1 runs as filler pieces in the bubbles of evaluation i (bd_stream.cuh, FILLERS).
-static int g_head_fillers = 1;
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+static int g_head_fillers = env_int("BD_HEAD_FILLERS", 1);  // env: debugging aid (tests run both policies explicitly)
 static int g_head_fill_row_kb = 22;   // k-blocks (of 128 weight rows x 64) wanted in a slot that hides a row op
 static int g_head_fill_gemm_kb = 8;   // ... in a slot that hides a GEMM -> GEMM boundary
 

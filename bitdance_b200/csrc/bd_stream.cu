@@ -755,7 +755,8 @@ constexpr uint32_t kTmemCols = 512;    //   2 collects the pieces of a filler pa
 
 struct StreamSmem {
   static constexpr int kRing = kStreamSlots * kStepBytes;
-  static constexpr int kBars = (2 * kStreamSlots + 2 * kAccBufs + 1) * 8;  // rings, accumulators, + the epilogue warps' own bulk-copy barrier
+  // rings, accumulators, the epilogue warps' own bulk-copy barrier, + the scratch handshake (A ring lent to an executor)
+  static constexpr int kBars = (2 * kStreamSlots + 2 * kAccBufs + 1 + 2) * 8;
   static constexpr int kBias = kAccBufs * 256;  // one pass's bias slice (<= 128 bf16) per accumulator buffer
   static constexpr int kMisc = 256;      // barriers (<= 168 B), TMEM slot at +192, reduction scratch at +208
   static_assert(kBars <= 192, "barrier area");
@@ -836,6 +837,16 @@ __device__ __forceinline__ GemmWork gemm_work(const StreamOp& op, int G, int c) 
 }
 __device__ __forceinline__ bool op_skipped(const StreamProgram& prog, const StreamOp& op, int it) {
   return (op.flags & kFlagSkipLast) && it == prog.n_iter - 1;
+}
+
+// The attention executor and the final-row executor borrow the A ring as scratch. Without fillers nothing can be in flight
+// there (the A producer is parked at the next GEMM's grid barrier); with fillers — GEMM work without dependencies — the A
+// producer could be streaming a piece's operand into the ring at that very moment (always in a CTA that has no share of
+// the GEMM before the op, e.g. small models). So the ring is handed over explicitly: the A producer drains it, signals
+// scr_free, and resumes only after the executors signal scr_done.
+__device__ __forceinline__ bool op_uses_scratch(const StreamProgram& prog, const StreamOp& op, int c) {
+  if (op.kind == kOpAttn) return c < (prog.M / op.i0) * (op.N / op.K);
+  return op.kind == kOpRow && op.sub == kRowFinal && c < prog.M;
 }
 
 // The weight stream of one CTA as a flat sequence of steps (op after op, pass after pass, k rotation inside a pass): two
@@ -925,6 +936,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
   uint64_t* acc_full = empty_a + kStreamASlots;
   uint64_t* acc_empty = acc_full + kAccBufs;
   uint64_t* aux_bar = acc_empty + kAccBufs;
+  uint64_t* scr_free = aux_bar + 1;   // A producer -> executors: the A ring is drained and stays untouched
+  uint64_t* scr_done = aux_bar + 2;   // executors -> A producer: scratch use finished
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + StreamSmem::kRing + 192);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);
   __nv_bfloat16* bias_s = reinterpret_cast<__nv_bfloat16*>(smem + StreamSmem::kRing + StreamSmem::kMisc);  // 16-byte aligned
@@ -948,6 +961,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
       mbar_init(&acc_empty[s], 4);
     }
     mbar_init(aux_bar, 1);
+    mbar_init(scr_free, 1);
+    mbar_init(scr_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -988,9 +1003,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
     if (elect_one()) {
       RingPos ar(kStreamASlots);
       OpCursor cur(prog, total);
+      uint32_t scr_uses = 0;
       while (cur.next()) {
         const StreamOp& op = prog.ops[cur.idx];
-        if (op.kind != kOpGemm) continue;
+        if (op.kind != kOpGemm) {
+          if (op_uses_scratch(prog, op, c)) {
+            // drain: every slot's latest fill has been consumed by the MMAs (slots before ar.slot were filled in round
+            // ar.round, the others one round earlier)
+            for (uint32_t s2 = 0; s2 < kStreamASlots; ++s2) {
+              if (s2 < ar.slot) mbar_wait(&empty_a[s2], ar.round & 1u);
+              else if (ar.round > 0) mbar_wait(&empty_a[s2], (ar.round & 1u) ^ 1u);
+            }
+            mbar_arrive(scr_free);
+            mbar_wait(scr_done, scr_uses & 1u);
+            ++scr_uses;
+          }
+          continue;
+        }
         if (op_skipped(prog, op, cur.it)) continue;
         const GemmWork gw = gemm_work(op, G, c);
         if (!gw.any()) continue;
@@ -1089,7 +1118,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
     const int lane = tid & 31;
     const int qd = warp & 3;
     const int m = qd * 32 + lane;
-    uint32_t pi = 0, pf = 0, aux_uses = 0;
+    uint32_t pi = 0, pf = 0, aux_uses = 0, scr_uses = 0;
     OpCursor cur(prog, total);
     while (cur.next()) {
       const int q = cur.q, it = cur.it;
@@ -1178,6 +1207,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           if (tid == 0) grid_wait(prog.sync, wait_target(op.wait_prev, cur.mseq, G), static_cast<unsigned int>(prog.poll_ns));
           epi_bar();
         }
+        const bool scratch = op_uses_scratch(prog, op, c);
+        if (scratch) mbar_wait(scr_free, scr_uses & 1u);  // the A ring is ours (see op_uses_scratch)
         if (op.kind == kOpRow) {
           row_op(prog, op, it, c, tid, red, smem_a);
         } else {
@@ -1190,6 +1221,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         }
         // generic-proxy writes to the A ring (attention tiles / final row) before later async-proxy (bulk copy) writes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (scratch) {
+          epi_bar();
+          if (tid == 0) mbar_arrive(scr_done);
+          ++scr_uses;
+        }
       }
       if (filler) continue;  // outside the barrier protocol: its consumers sit behind a later full barrier
       // ---- this CTA's part of op q is complete: publish ----

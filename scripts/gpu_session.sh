@@ -10,10 +10,12 @@ for step in "$@"; do
   case "$step" in
     stream)   timeout 600 python -m pytest tests/test_stream_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/${TAG}_test_stream.log ;;
     head)     timeout 900 python -m pytest tests/test_head_gpu.py -m gpu -q -s 2>&1 | grep -v "^    \|^$" | tail -150 > gpurun_out/${TAG}_test_head.log ;;
-    tests)    timeout 2400 python -m pytest tests -m gpu -q -s 2>&1 | tail -150 > gpurun_out/${TAG}_tests.log ;;
+    head0)    BD_HEAD_FILLERS=0 timeout 900 python -m pytest tests/test_head_gpu.py -m gpu -q -s -k "stream" 2>&1 | grep -v "^    \|^$" | tail -150 > gpurun_out/${TAG}_test_head_fill0.log ;;
+    tests)    timeout 2400 python -m pytest tests -m gpu -q -s 2>&1 | grep -v "^    " > gpurun_out/${TAG}_tests.log ;;
     timeline) timeout 900 python scripts/head_timeline.py > gpurun_out/${TAG}_head_timeline.txt 2>&1 ;;
     ab)       timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab.txt 2>&1 ;;
     ab_r01)   BD_LIB_PATH=$PWD/ab/libbitdance_b200_r01.so timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab_r01.txt 2>&1 ;;
+    diag)     timeout 600 python scripts/head_diag.py > gpurun_out/${TAG}_head_diag.txt 2>&1 ;;
     ae)       timeout 900 python scripts/ae_bench.py > gpurun_out/${TAG}_ae_bench.txt 2>&1 ;;
     bench)    timeout 1500 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
     benchref) timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err ;;

@@ -109,4 +109,26 @@ for mode in modes.split(","):
         t_prev = done
     print("third evaluation, per op kind (us):", {k: round(v, 1) for k, v in tot.items()}, "total",
           round(sum(tot.values()), 1))
+    # phases of the GEMM ops (median over CTAs with work): A loads start -> first MMA -> last MMA issued -> accumulator ready
+    # -> first chunk loaded -> first chunk stored -> epilogue done -> arrival published; and the op's last arrival
+    print("GEMM op phases, third evaluation (us, medians over CTAs): dep->A  A->MMA1  MMA  ->acc  ->ld1  chunk1  ->epi  ->arrive | last arrival - median arrival")
+    for q in range(len(pre) + 2 * len(body), nops):
+        nm = names[q]
+        if isinstance(nm, tuple) or nm.split(".")[-1] not in ("wqkv", "wo", "w1", "w2", "input_proj", "ada"):
+            continue
+        st = d[q]
+        ok = (st[:, 0] > 0) & (st[:, 5] > 0) & (st[:, 1] > 0)
+        if not ok.any():
+            continue
+        st = st[ok]
+        prev_done = d[q - 1, :, 5]
+        k = q - 1
+        while isinstance(names[k], tuple):
+            k -= 1
+        prev_done = d[k, :, 5][d[k, :, 5] > 0].max().item()
+        med = lambda a: a.median().item()
+        seg = [med(st[:, 0]) - prev_done, med(st[:, 1] - st[:, 0]), med(st[:, 2] - st[:, 1]), med(st[:, 3] - st[:, 2]),
+               med(st[:, 6] - st[:, 3]) if (st[:, 6] > 0).all() else float("nan"),
+               med(st[:, 7] - st[:, 6]) if (st[:, 7] > 0).all() else float("nan"), med(st[:, 4] - st[:, 3]), med(st[:, 5] - st[:, 4])]
+        print(f"  {nm:12s} " + " ".join(f"{x:7.2f}" for x in seg) + f" | {st[:, 5].max().item() - med(st[:, 5]):5.2f}")
 ops.head_set_fillers(1)
