@@ -29,7 +29,7 @@ __device__ __forceinline__ void store_bf16x8(uint8_t* outb, const StreamOp& op, 
 
 template <int NC>
 __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m, int n, const float (&acc)[NC],
-                                               int split, int mode, const __nv_bfloat16* bias_sm) {
+                                               int split, int mode, const float* bias_sm) {
   if (m >= M) return;
   if (mode & 2) {  // experiment: no stores (keep the data dependency alive)
     float t = 0.f;
@@ -51,14 +51,13 @@ __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m,
     }
     return;
   }
+  // the bias slice of this pass sits in shared memory as fp32 (staged before the accumulator was ready)
   float b[NC];
-  if (bias_sm && !(mode & 1)) {  // this pass's bias slice, staged in shared memory before the accumulator was ready
+  if (bias_sm && !(mode & 1)) {
 #pragma unroll
-    for (int j = 0; j < NC / 8; ++j) {
-      float t[8];
-      bf16x8_to_f(*reinterpret_cast<const uint4*>(bias_sm + 8 * j), t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) b[8 * j + i] = t[i];
+    for (int j = 0; j < NC / 4; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(bias_sm + 4 * j);
+      b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
     }
   } else {
 #pragma unroll
@@ -74,7 +73,8 @@ __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m,
       for (int j = 0; j < 8; ++j) {
         const float g = bf16_round(acc[16 * u + j] + b[16 * u + j]);
         const float up = bf16_round(acc[16 * u + 8 + j] + b[16 * u + 8 + j]);
-        y[u][j] = bf16_round(siluf_(g)) * up;
+        // silu with the fast reciprocal (error ~2 fp32 ulps, far below the bf16 rounding that follows)
+        y[u][j] = bf16_round(__fdividef(g, 1.0f + __expf(-g))) * up;
       }
     }
     if constexpr (NC == 32) store_bf16x16(outb, op, m, n >> 1, y[0], y[1]);  // n % 32 == 0 here: a whole sector
@@ -82,14 +82,22 @@ __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m,
     return;
   }
   float y[NC / 8][8];
+  if (op.act == kActNone) {
+    // one rounding: bf16(acc + bias) is produced by the pack itself (an explicit bf16_round first would be idempotent)
 #pragma unroll
-  for (int u = 0; u < NC / 8; ++u) {
+    for (int u = 0; u < NC / 8; ++u)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = bf16_round(acc[8 * u + j] + b[8 * u + j]);
-      if (op.act == kActSilu) v = bf16_round(siluf_(v));
-      if (op.act == kActGeluTanh) v = bf16_round(gelu_tanhf_(v));
-      y[u][j] = v;
+      for (int j = 0; j < 8; ++j) y[u][j] = acc[8 * u + j] + b[8 * u + j];
+  } else {
+#pragma unroll
+    for (int u = 0; u < NC / 8; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = bf16_round(acc[8 * u + j] + b[8 * u + j]);
+        if (op.act == kActSilu) v = bf16_round(siluf_(v));
+        if (op.act == kActGeluTanh) v = bf16_round(gelu_tanhf_(v));
+        y[u][j] = v;
+      }
     }
   }
 #pragma unroll
@@ -757,7 +765,7 @@ struct StreamSmem {
   static constexpr int kRing = kStreamSlots * kStepBytes;
   // rings, accumulators, the epilogue warps' own bulk-copy barrier, + the scratch handshake (A ring lent to an executor)
   static constexpr int kBars = (2 * kStreamSlots + 2 * kAccBufs + 1 + 2) * 8;
-  static constexpr int kBias = kAccBufs * 256;  // one pass's bias slice (<= 128 bf16) per accumulator buffer
+  static constexpr int kBias = kAccBufs * 512;  // one pass's bias slice (<= 128 values, fp32) per accumulator buffer
   static constexpr int kMisc = 256;      // barriers (<= 168 B), TMEM slot at +192, reduction scratch at +208
   static_assert(kBars <= 192, "barrier area");
   static constexpr int kTotal = kRing + kMisc + kBias + 1024 /*align slack*/;
@@ -940,7 +948,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
   uint64_t* scr_done = aux_bar + 2;   // executors -> A producer: scratch use finished
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + StreamSmem::kRing + 192);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);
-  __nv_bfloat16* bias_s = reinterpret_cast<__nv_bfloat16*>(smem + StreamSmem::kRing + StreamSmem::kMisc);  // 16-byte aligned
+  float* bias_s = reinterpret_cast<float*>(smem + StreamSmem::kRing + StreamSmem::kMisc);  // 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int c = blockIdx.x;
@@ -1156,11 +1164,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           const uint32_t par = gw.piece ? (pf & 1u) : ((pi >> 1) & 1u);
           // bias slice of this pass -> shared memory while the MMAs are still running (a global load per chunk after the
           // accumulator is ready would put an L2 round trip — there is no L1 left — on the dependency path)
-          const __nv_bfloat16* bias_sm = nullptr;
+          const float* bias_sm = nullptr;
           if (op.p2 && op.sub != kEpiPartial) {
-            if (tid < w / 8)
-              reinterpret_cast<uint4*>(bias_s + buf * 128)[tid] =
-                  *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(op.p2) + n0 + tid * 8);
+            if (tid < w / 8) {
+              float t8[8];
+              bf16x8_to_f(ldg_u4(reinterpret_cast<const __nv_bfloat16*>(op.p2) + n0 + tid * 8), t8);
+              float4* dst4 = reinterpret_cast<float4*>(bias_s + buf * 128 + tid * 8);
+              dst4[0] = make_float4(t8[0], t8[1], t8[2], t8[3]);
+              dst4[1] = make_float4(t8[4], t8[5], t8[6], t8[7]);
+            }
             epi_bar();
             bias_sm = bias_s + buf * 128;
           }

@@ -187,3 +187,46 @@ def test_mlpconnector_module(pipe, model_dir):
     ref = bf(h @ bf(sd["fc2.weight"]).t() + bf(sd["fc2.bias"]))
     assert y.shape == (2, 16, 256)
     assert (y - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item() + 1e-3
+
+
+def test_mllm_surface(pipe, model_dir):
+    """``modeling.mllm.MLLModel`` (mllm.py:387-501, 899-941): gen_image_block_causal gives exactly the pipeline's image
+    for the same seed / noise; encode_image = tokenizer bits -> MLPconnector -> + 2-D pos-embed against the oracle."""
+    from modeling.mllm import MLLModel
+    from oracle import ae as oa
+    info = model_dir[1]
+    sds, m = info["sds"], info["model"]
+    mll = MLLModel.from_pipeline(pipe)
+    assert mll.parallel_num == m["parallel_num"] and mll.config.vit_patch_size == pipe.vae_patch_size
+    kw = dict(guidance_scale=3.0, num_sampling_steps=3, max_length=64, num_images=1, image_size=[32, 32])
+    torch.manual_seed(5)
+    a = mll.gen_image("user\na photo of a cat", "assistant\n", **kw)
+    torch.manual_seed(5)
+    b = pipe.gen_image("user\na photo of a cat", "assistant\n", **kw)
+    assert a.shape == (1, 3, 32, 32) and torch.equal(a, b)
+    with pytest.raises(NotImplementedError):
+        mll.forward_train()
+    # encode_image: two images of different sizes -> packed context
+    torch.manual_seed(6)
+    imgs = [torch.rand(1, 3, 32, 48) * 2 - 1, torch.rand(1, 3, 16, 16) * 2 - 1]
+    emb, lat = mll.encode_image([x.cuda() for x in imgs])
+    n_tok = (32 // 4) * (48 // 4) + (16 // 4) * (16 // 4)
+    assert emb.shape == (n_tok, 256) and emb.dtype == torch.float32 and lat.shape == (n_tok, 32)
+    ps = pipe.ps
+    bf = lambda t: t.to(torch.bfloat16).float()
+    off = 0
+    for x in imgs:
+        with torch.no_grad():
+            q_ref, lat_ref = oa.encode(sds["ae"], x, rnd=oa.bf16)
+        C, H, W = q_ref.shape[1:]
+        # 'c (h p1) (w p2) -> (h w p1 p2) c'
+        ref_tok = q_ref[0].view(C, H // ps, ps, W // ps, ps).permute(1, 3, 2, 4, 0).reshape(-1, C)
+        got = lat[off:off + H * W].float().cpu()
+        assert (got == ref_tok).float().mean().item() > 0.97
+        # the connector + pos-embed on the GPU's own bits
+        p = sds["proj"]
+        hid = bf(torch.nn.functional.gelu(bf(bf(got) @ bf(p["fc1.weight"]).t() + bf(p["fc1.bias"])), approximate="tanh"))
+        ref = bf(hid @ bf(p["fc2.weight"]).t() + bf(p["fc2.bias"])) + mll.get_2d_embed(H, W, ps=ps).cpu()
+        e = (emb[off:off + H * W].cpu() - ref).abs().max().item()
+        assert e <= 1.5e-2 * ref.abs().max().item() + 1e-3, e
+        off += H * W
