@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const void* __restrict__ x
 //   rope tables: fp32 [max_pos, hd] (cos | sin of cat(freqs, freqs), built by torch exactly like Qwen3RotaryEmbedding)
 //   ROPE_F32 (AR steps): rot = q*cos + rotate_half(q)*sin in fp32 (unfused), then bf16 (the SDPA autocast cast)
 //   else (prefill):      cos/sin rounded to bf16, every product and the sum round to bf16
-template <int HD, bool ROPE_F32>
+//   ROPE_PAIRS (ImageNet class-conditional model, imagenet_gen/src/layers_parallel.py:255-290): no q/k RMSNorm (qn_w / kn_w
+//   NULL), interleaved (even, odd) pairs rotated by the angle of table entry [pos][pair] (rope_cos / rope_sin are
+//   [max_pos, hd/2] here: the 2-D RoPE table of precompute_freqs_cis_2d, half of the pairs turn with x, half with y), fp32
+//   arithmetic, one rounding to bf16 (apply_rotary_emb computes in fp32 and casts back, :273-290)
+template <int HD, bool ROPE_F32, bool ROPE_PAIRS = false>
 __global__ void __launch_bounds__(256) qk_norm_rope_append_kernel(
     const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ qn_w, const __nv_bfloat16* __restrict__ kn_w,
     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, const int* __restrict__ seq_lens,
@@ -141,6 +145,20 @@ __global__ void __launch_bounds__(256) qk_norm_rope_append_kernel(
   if (!is_q && !is_k) {  // V: plain copy
 #pragma unroll
     for (int j = 0; j < VPT; ++j) dst[lane * VPT + j] = __float2bfloat16_rn(x[j]);
+    return;
+  }
+  if (ROPE_PAIRS) {
+    // lane holds VPT consecutive elements = VPT / 2 whole (even, odd) pairs: the rotation is lane-local
+    float y[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; j += 2) {
+      const int pr = (lane * VPT + j) >> 1;
+      const float c = rope_cos[static_cast<long long>(pos) * (HD / 2) + pr], sn = rope_sin[static_cast<long long>(pos) * (HD / 2) + pr];
+      y[j] = __fsub_rn(__fmul_rn(x[j], c), __fmul_rn(x[j + 1], sn));
+      y[j + 1] = __fadd_rn(__fmul_rn(x[j + 1], c), __fmul_rn(x[j], sn));
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) dst[lane * VPT + j] = __float2bfloat16_rn(y[j]);
     return;
   }
   // RMSNorm over the head (bf16 in -> bf16 out): bf16(w * bf16(x * rstd))
@@ -345,6 +363,10 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
   const bool pdl = (flags & 1) != 0;
   const int M = R * S, D = w.D, hd = w.head_dim;
   const int qkv_n = (w.Hq + 2 * w.Hkv) * hd;
+  const bool rope_pairs = (w.variant & BD_LLM_ROPE_PAIRS) != 0;
+  for (int li = 0; li < w.n_layers; ++li)  // q/k RMSNorm weights are optional only for the pair-RoPE (ImageNet) variant
+    BD_REQUIRE(rope_pairs || (w.layers[li].q_norm_w && w.layers[li].k_norm_w));
+  BD_REQUIRE(!rope_pairs || stream_f32);  // that model keeps an fp32 residual stream throughout
   const LlmWs L = llm_ws_layout(w, M, R, S, attn_splits);
   if (workspace_bytes < L.total) return BD_ERR_WORKSPACE;
   BD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
@@ -394,9 +416,16 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
     return next_norm ? norm_to_bf16(next_norm) : BD_OK;
   };
 
+  if (w.emb_norm_w) {
+    // BitDance.forward_model (imagenet_gen/src/model_parallel.py:343-350): x = emb_norm(x) before the first block, in place
+    BD_REQUIRE(stream_f32);
+    BD_TRY(launch_k(rmsnorm_kernel<true, true>, dim3(M), dim3(256), 0, st, pdl, (const void*)hidden, bf(w.emb_norm_w), hidden,
+                    D, w.eps, (const float*)nullptr, 1));
+  }
+
   // ---- AR block of one 128-row tile with stream-packed weights: the Linears / residual adds / norms of every layer run as
   // persistent bd_stream_kernel segments; RoPE + KV append and the paged attention stay the kernels below ----
-  if (w.stream_ctas > 0 && stream_f32 && !causal && M <= 128 && w.stream_ctas == num_sms() && w.stream_ctas >= M &&
+  if (w.stream_ctas > 0 && stream_f32 && !causal && !rope_pairs && M <= 128 && w.stream_ctas == num_sms() && w.stream_ctas >= M &&
       (qkv_n % 16) == 0 &&
       D <= 6144 && (w.I % 64) == 0) {
     // blocked operands are read in whole 128-row x 64-column tiles: padding rows / columns must be finite
@@ -440,25 +469,14 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
       const long long warps = static_cast<long long>(M) * (w.Hq + 2 * w.Hkv);
       const unsigned grid = static_cast<unsigned>((warps * 32 + 255) / 256);
       int rc;
-      if (hd == 128) {
-        rc = stream_f32 ? launch_k(qk_norm_rope_append_kernel<128, true>, dim3(grid), dim3(256), 0, st, pdl,
-                                   (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
-                                   (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq,
-                                   w.Hkv, w.eps, M)
-                        : launch_k(qk_norm_rope_append_kernel<128, false>, dim3(grid), dim3(256), 0, st, pdl,
-                                   (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
-                                   (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq,
-                                   w.Hkv, w.eps, M);
-      } else {
-        rc = stream_f32 ? launch_k(qk_norm_rope_append_kernel<64, true>, dim3(grid), dim3(256), 0, st, pdl,
-                                   (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
-                                   (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq,
-                                   w.Hkv, w.eps, M)
-                        : launch_k(qk_norm_rope_append_kernel<64, false>, dim3(grid), dim3(256), 0, st, pdl,
-                                   (const __nv_bfloat16*)qkv, bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin,
-                                   (const int*)seq_lens, (const int*)page_table, max_pages, q, kpool, vpool, S, w.Hq,
-                                   w.Hkv, w.eps, M);
-      }
+#define BD_QK_LAUNCH(HD_, F32_, PAIRS_)                                                                                  \
+  launch_k(qk_norm_rope_append_kernel<HD_, F32_, PAIRS_>, dim3(grid), dim3(256), 0, st, pdl, (const __nv_bfloat16*)qkv,  \
+           bf(lw.q_norm_w), bf(lw.k_norm_w), rope_cos, rope_sin, (const int*)seq_lens, (const int*)page_table, max_pages, \
+           q, kpool, vpool, S, w.Hq, w.Hkv, w.eps, M)
+      if (rope_pairs) rc = hd == 128 ? BD_QK_LAUNCH(128, true, true) : BD_QK_LAUNCH(64, true, true);
+      else if (hd == 128) rc = stream_f32 ? BD_QK_LAUNCH(128, true, false) : BD_QK_LAUNCH(128, false, false);
+      else rc = stream_f32 ? BD_QK_LAUNCH(64, true, false) : BD_QK_LAUNCH(64, false, false);
+#undef BD_QK_LAUNCH
       BD_TRY(rc);
     }
     // keys visible to block b: seq_lens[b] (past) + S (this block), read on the device by the attention kernel

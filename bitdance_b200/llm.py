@@ -24,8 +24,10 @@ class LlmLayer(C.Structure):
 
 class LlmWeights(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("D", "I", "n_layers", "Hq", "Hkv", "head_dim")] + [
-        ("eps", C.c_float), ("w_tiled", C.c_int), ("stream_ctas", C.c_int), ("reserved_", C.c_int),
-        ("final_norm_w", C.c_void_p), ("layers", C.POINTER(LlmLayer))]
+        ("eps", C.c_float), ("w_tiled", C.c_int), ("stream_ctas", C.c_int), ("variant", C.c_int),
+        ("final_norm_w", C.c_void_p), ("layers", C.POINTER(LlmLayer)), ("emb_norm_w", C.c_void_p)]
+
+ROPE_PAIRS = 1  # BD_LLM_ROPE_PAIRS (include/bitdance_b200.h)
 
 
 def llm_config_dict(cfg) -> dict:
@@ -74,10 +76,13 @@ class KVCache:
 
 class LlmRunner:
     def __init__(self, state_dict: dict | None, cfg, device="cuda", prefix="model.", synthetic_seed: int | None = None,
-                 max_positions: int = 8192, stream: bool | None = None):
+                 max_positions: int = 8192, stream: bool | None = None, qk_norm: bool = True,
+                 rope_pairs: tuple | None = None, emb_norm: torch.Tensor | None = None):
         """stream: also keep stream-major copies of the four Linears of every layer, so that AR blocks of one 128-row tile
         run their GEMMs / residual adds / RMSNorms as persistent bd_stream_kernel segments (costs a second copy of the
-        decoder weights in HBM: 26 GB for Qwen3-14B)."""
+        decoder weights in HBM: 26 GB for Qwen3-14B).
+        qk_norm=False / rope_pairs=(cos, sin) fp32 [positions, head_dim/2] / emb_norm=[D]: the ImageNet class-conditional
+        decoder variant (no q/k RMSNorm, interleaved-pair 2-D RoPE from a table, RMSNorm on the input embeddings)."""
         self.cfg = c = llm_config_dict(cfg)
         self.device = dev = torch.device(device)
         D, I, hd = c["hidden_size"], c["intermediate_size"], c["head_dim"]
@@ -113,8 +118,8 @@ class LlmRunner:
             keep = self._keep
             ln1 = get(p + "input_layernorm.weight", (D,), one=True)
             ln2 = get(p + "post_attention_layernorm.weight", (D,), one=True)
-            qn = get(p + "self_attn.q_norm.weight", (hd,), one=True)
-            kn = get(p + "self_attn.k_norm.weight", (hd,), one=True)
+            qn = get(p + "self_attn.q_norm.weight", (hd,), one=True) if qk_norm else None
+            kn = get(p + "self_attn.k_norm.weight", (hd,), one=True) if qk_norm else None
             wqkv = torch.cat([get(p + "self_attn.q_proj.weight", (Hq * hd, D)),
                               get(p + "self_attn.k_proj.weight", (Hkv * hd, D)),
                               get(p + "self_attn.v_proj.weight", (Hkv * hd, D))], dim=0).contiguous()
@@ -133,7 +138,8 @@ class LlmRunner:
             del gate, up
             wqkv, wo, wgu, wd = (ops.pack_weight(t).data for t in (wqkv, wo, wgu, wd))  # tile-major for HBM streaming
             keep += [ln1, ln2, qn, kn, wqkv, wo, wgu, wd]
-            lw.ln1_w, lw.ln2_w, lw.q_norm_w, lw.k_norm_w = ln1.data_ptr(), ln2.data_ptr(), qn.data_ptr(), kn.data_ptr()
+            lw.ln1_w, lw.ln2_w = ln1.data_ptr(), ln2.data_ptr()
+            lw.q_norm_w, lw.k_norm_w = (qn.data_ptr(), kn.data_ptr()) if qk_norm else (None, None)
             lw.wqkv, lw.wo, lw.w_gate_up, lw.w_down = wqkv.data_ptr(), wo.data_ptr(), wgu.data_ptr(), wd.data_ptr()
         fn = get("norm.weight", (D,), one=True)
         self._keep.append(fn)
@@ -144,14 +150,25 @@ class LlmRunner:
         w.w_tiled = 1
         w.stream_ctas = n_ctas
         w.final_norm_w = fn.data_ptr()
+        w.variant = ROPE_PAIRS if rope_pairs is not None else 0
+        if emb_norm is not None:
+            en = emb_norm.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+            self._keep.append(en)
+            w.emb_norm_w = en.data_ptr()
         self._layers = layers
         w.layers = C.cast(layers, C.POINTER(LlmLayer))
         self.w = w
         self._ws = None
-        self._build_rope(max_positions)
+        if rope_pairs is not None:
+            cos, sin = rope_pairs
+            assert cos.shape == sin.shape and cos.shape[1] == hd // 2
+            self.rope_cos = cos.detach().to(device=dev, dtype=torch.float32).contiguous()
+            self.rope_sin = sin.detach().to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            self._build_rope(max_positions)
 
     def param_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self._keep)
+        return sum(t.numel() * t.element_size() for t in self._keep if t is not None)
 
     def _build_rope(self, n):
         # Qwen3RotaryEmbedding: inv_freq = 1 / theta^(arange(0,d,2)/d); emb = cat(freqs, freqs); fp32 cos/sin

@@ -214,10 +214,16 @@ typedef struct {
   int stream_ctas;              /* > 0: the *_s weights exist, packed for this many CTAs: fp32-stream, non-causal passes with
                                  * R*S <= 128 run every layer's four Linears, residual adds and RMSNorms as persistent
                                  * bd_stream_kernel segments (RoPE / KV append / paged attention stay separate kernels) */
-  int reserved_;
+  int variant;                  /* 0: Qwen3 (q/k RMSNorm over head_dim, rotate_half RoPE, tables fp32 [pos, head_dim]);
+                                 * BD_LLM_ROPE_PAIRS: the ImageNet class-conditional decoder (imagenet_gen/src/
+                                 * layers_parallel.py): no q/k norm (q_norm_w / k_norm_w NULL), interleaved-pair RoPE in fp32
+                                 * with tables [pos, head_dim/2] (the 2-D table of precompute_freqs_cis_2d), fp32 stream only */
   const void* final_norm_w;     /* bf16 [D] */
   const bd_llm_layer_t* layers; /* HOST array [n_layers] */
+  const void* emb_norm_w;       /* bf16 [D] or NULL: RMSNorm applied to the input embeddings in place before the first
+                                 * layer (BitDance.forward_model, imagenet_gen/src/model_parallel.py:343-345) */
 } bd_llm_weights_t;
+#define BD_LLM_ROPE_PAIRS 1
 
 /* Qwen3Model.forward(inputs_embeds, past_key_values, attention_mask) as the reference calls it at
  * modeling/t2i_pipeline.py:199,211,224,229 (prefill) and :261,266 (AR block) — third-party transformers==4.57.0.

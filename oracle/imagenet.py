@@ -10,8 +10,11 @@ Functional restatement (state-dict in, tensors out) of SURVEY.md §8 row a16 —
 The diffusion head is the same network as the T2I one with ``head_dim=64`` and no output sigmoid
 (``imagenet_gen/src/diff_head_parallel.py``), i.e. ``oracle/head.py`` with those two switches.
 
-Exact fp32 math (``rnd=ident``); the autocast rounding policy of the CUDA path will be added with the CUDA driver for
-this row (next round). Pinned against the unmodified reference in ``tests/test_oracle_vs_reference.py``.
+``rnd=ident``: exact fp32 math, pinned bit-exactly (token grid) against the unmodified reference in
+``tests/test_oracle_vs_reference.py``. ``rnd=bf16``: the policy of the reference's deployment — fp32 weights under
+``torch.amp.autocast("cuda", bfloat16)`` (sample_ddp_parallel.py:158): every Linear / matmul rounds its inputs and output
+to bf16 (fp32 accumulate), RMSNorm, the residual stream, RoPE, the additive mask and softmax run in fp32, ``q * scale``
+and ``apply_rotary_emb(...).type_as(x)`` round to bf16; the KV cache holds bf16 values.
 """
 from __future__ import annotations
 
@@ -94,43 +97,48 @@ def make_buffers(cfg: dict):
     return fc[:-pn], mask, h, w
 
 
-def block_onestep(sd, prefix, x, mask, fc, cache, start, end, n_head):
+def _lin(x, w, b, rnd):
+    y = rnd(x) @ rnd(w.float()).t()
+    return rnd(y + rnd(b.float())) if b is not None else rnd(y)
+
+
+def block_onestep(sd, prefix, x, mask, fc, cache, start, end, n_head, rnd=oh.ident):
     """TransformerBlock.forward_onestep with the static KV cache (keys / values written at [start, end))."""
     B, S, dim = x.shape
     hd = dim // n_head
     a = rmsnorm(x, sd[prefix + "attention_norm.weight"])
-    q, k, v = (a @ sd[prefix + "attention.wqkv.weight"].t()).chunk(3, dim=-1)
+    q, k, v = _lin(a, sd[prefix + "attention.wqkv.weight"], None, rnd).chunk(3, dim=-1)
     q, k, v = (t.view(B, S, n_head, hd) for t in (q, k, v))
-    q, k = apply_rotary(q, fc), apply_rotary(k, fc)
+    q, k = rnd(apply_rotary(q, fc)), rnd(apply_rotary(k, fc))
     q, k, v = (t.transpose(1, 2) for t in (q, k, v))
     cache[0][:, :, start:end] = k
     cache[1][:, :, start:end] = v
     keys, values = cache[0][:, :, :end], cache[1][:, :, :end]
-    att = (q * hd ** -0.5) @ keys.transpose(-1, -2)
+    att = rnd(rnd(q * hd ** -0.5) @ keys.transpose(-1, -2))
     if att.shape[-2] > 1:
         att = att + mask
-    o = (torch.softmax(att, dim=-1) @ values).transpose(1, 2).reshape(B, S, dim)
-    h = x + o @ sd[prefix + "attention.wo.weight"].t()
+    o = rnd(rnd(torch.softmax(att.float(), dim=-1)) @ values).transpose(1, 2).reshape(B, S, dim)
+    h = x + _lin(o, sd[prefix + "attention.wo.weight"], None, rnd)
     f = rmsnorm(h, sd[prefix + "ffn_norm.weight"])
-    h1, h2 = (f @ sd[prefix + "feed_forward.w1.weight"].t()).chunk(2, dim=-1)
-    return h + (F.silu(h1) * h2) @ sd[prefix + "feed_forward.w2.weight"].t()
+    h1, h2 = _lin(f, sd[prefix + "feed_forward.w1.weight"], None, rnd).chunk(2, dim=-1)
+    return h + _lin(rnd(rnd(F.silu(h1)) * h2), sd[prefix + "feed_forward.w2.weight"], None, rnd)
 
 
-def forward_model(sd, cfg, x, mask, fc, caches, start, end):
-    x = rmsnorm(x, sd["emb_norm.weight"])
+def forward_model(sd, cfg, x, mask, fc, caches, start, end, rnd=oh.ident):
+    x = rmsnorm(x.float(), sd["emb_norm.weight"])
     for i in range(cfg["n_layer"]):
-        x = block_onestep(sd, f"layers.{i}.", x, mask, fc[start:end], caches[i], start, end, cfg["n_head"])
+        x = block_onestep(sd, f"layers.{i}.", x, mask, fc[start:end], caches[i], start, end, cfg["n_head"], rnd)
     return rmsnorm(x, sd["norm.weight"])
 
 
-def proj_in(sd, x):
+def proj_in(sd, x, rnd=oh.ident):
     """MLPConnector (SwiGLU, with biases)."""
-    h1, h2 = (x @ sd["proj_in.w1.weight"].t() + sd["proj_in.w1.bias"]).chunk(2, dim=-1)
-    return (F.silu(h1) * h2) @ sd["proj_in.w2.weight"].t() + sd["proj_in.w2.bias"]
+    h1, h2 = _lin(x, sd["proj_in.w1.weight"], sd["proj_in.w1.bias"], rnd).chunk(2, dim=-1)
+    return _lin(rnd(rnd(F.silu(h1)) * h2), sd["proj_in.w2.weight"], sd["proj_in.w2.bias"], rnd)
 
 
 def sample(sd: dict, cfg: dict, class_ids: torch.Tensor, sample_steps: int, cfg_scale: float, noise, *,
-           cfg_schedule: str = "linear"):
+           cfg_schedule: str = "linear", rnd=oh.ident, trace: list | None = None):
     """BitDance.sample up to (not including) ``vae.decode``.
 
     sd: the reference state dict (keys as in BitDance, without the ``vae.`` entries); cfg: dim, n_layer, n_head,
@@ -157,21 +165,25 @@ def sample(sd: dict, cfg: dict, class_ids: torch.Tensor, sample_steps: int, cfg_
         if i == 0:
             n0 = cls + pn - 1
             x = forward_model(sd, cfg, torch.cat([c, sd["query_token"].repeat(B, 1, 1)], dim=1), mask[:n0, :n0], fc,
-                              caches, 0, n0)
+                              caches, 0, n0, rnd)
         else:
             start = pn * (i - 1) + cls + pn - 1
-            x = forward_model(sd, cfg, proj_in(sd, last), mask[start:start + pn, :start + pn], fc, caches, start,
-                              start + pn)
+            x = forward_model(sd, cfg, proj_in(sd, last, rnd), mask[start:start + pn, :start + pn], fc, caches, start,
+                              start + pn, rnd)
         z = x[:, -pn:, :] + sd["pos_for_diff.weight"][i * pn:(i + 1) * pn, :]
+        if trace is not None:
+            trace.append(dict(z=z.clone()))
         if cfg_scale > 1.0:
             cfg_iter = cfg_scale if cfg_schedule == "constant" else 1.0 + (cfg_scale - 1.0) * i / steps
         else:
             cfg_iter = 1.0
         # head.sample -> euler_maruyama: with cfg_iter <= 1 the reference runs all B rows un-guided
-        pred = oh.euler_maruyama(head_sd, z, cfg_iter, sample_steps, noise[i], head_dim=64, out_sigmoid=False)
+        pred = oh.euler_maruyama(head_sd, z, cfg_iter, sample_steps, noise[i], head_dim=64, out_sigmoid=False, rnd=rnd)
         if cfg_iter > 1.0:
             pass  # euler_maruyama returns cat[x] * 2 already
         last = torch.sign(pred)
+        if trace is not None:
+            trace[-1]["last"] = last.clone()
         preds.append(last)
     tokens = torch.cat(preds, dim=-2)[:act]
     if cfg.get("parallel_mode", "patch") == "patch":
