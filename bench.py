@@ -193,6 +193,28 @@ def main():
     _lib.check(lib.bd_device_check(), "bd_device_check")
     eng, embed = build_synthetic_engine(args.model, dev, seed=rank)
     eng.use_graph = bool(args.graph)
+    collectives = {}
+    if world > 1:
+        # the two collectives of the sharded path, on NCCL over NVLink: a start-up broadcast of rank 0's
+        # prepacked weight set (what replaces N checkpoint reads), and — inside the e2e region below — one all-gather of the
+        # packed token grids per batch. Neither is on the per-step data path: replicas stay independent.
+        from bitdance_b200 import parallel
+        try:
+            ts = eng.weight_tensors() + [embed]
+            nbytes = sum(t.numel() * t.element_size() for t in ts)
+            dist.barrier()
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            parallel.broadcast_tensors(ts, src=0)
+            b1.record()
+            torch.cuda.synchronize()
+            tb = torch.tensor([b0.elapsed_time(b1)], device=dev)
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+            collectives["weight_broadcast"] = {"gb": nbytes / 1e9, "tensors": len(ts), "ms": tb.item(),
+                                               "gbs_per_receiver": nbytes / 1e9 / (tb.item() / 1e3)}
+        except Exception as e:
+            collectives["weight_broadcast"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     m = MODELS[args.model]
     pn, vps = m["parallel_num"], eng.vae_patch_size
     h, w = args.height // vps, args.width // vps
@@ -230,6 +252,11 @@ def main():
         imgs = pipe.generate(prompt, height=args.height, width=args.width, num_sampling_steps=S,
                              guidance_scale=args.guidance, num_images=B, seed=1234 + rank)
         assert len(imgs) == B and imgs[0].size == (args.width, args.height)
+        if world > 1:   # the finished (packed, 16 KB / image) token grids of every rank, one all-gather per batch
+            from bitdance_b200 import parallel
+            allg = parallel.gather_token_grids(pipe.last_packed_tokens)
+            collectives["token_grid_all_gather"] = {"bytes_per_rank": int(pipe.last_packed_tokens.numel() * 4),
+                                                    "gathered_shape": list(allg.shape)}
 
     ids_dev = ids_host.to(dev)
 
@@ -311,6 +338,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roof,
     }
+    if collectives:
+        line["collectives"] = collectives
     if not args.no_gpu_reference and world == 1:
         # SURVEY.md section 8d's "number to beat": the unmodified reference, eager PyTorch on this same B200 under CUDA
         # autocast (bounded: prefill + 1 warm-up + 3 timed AR steps, extrapolated like the CPU arm)

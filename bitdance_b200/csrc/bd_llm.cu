@@ -204,6 +204,7 @@ static int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, 
 }
 
 static size_t al(size_t v) { return (v + 255) & ~size_t(255); }
+constexpr int kLlmMaxSplits = 16;
 
 struct LlmWs {
   size_t a, qkv, q, o, g, attn, gemm, total;
@@ -224,7 +225,14 @@ static LlmWs llm_ws_layout(const bd_llm_weights_t& w, int M, int R, int S, int a
   L.q = take(static_cast<size_t>(M) * w.Hq * w.head_dim * 2);
   L.o = take(static_cast<size_t>(M) * w.Hq * w.head_dim * 2);
   L.g = take(static_cast<size_t>(M) * w.I * 2);
-  L.attn = take(attn_llm_workspace_bytes(R, S, w.Hq, w.head_dim, attn_splits));
+  {
+    size_t ab = attn_llm_workspace_bytes(R, S, w.Hq, w.head_dim, attn_splits);
+    if (w.layer_tab && w.stream_ctas > 0 && M <= 128) {  // in-engine attention: partials for up to kLlmMaxSplits key ranges
+      const size_t eb = static_cast<size_t>(kLlmMaxSplits) * R * w.Hq * S * (w.head_dim + 2) * sizeof(float);
+      ab = eb > ab ? eb : ab;
+    }
+    L.attn = take(ab);
+  }
   size_t gm = 0;
   auto gw = [&](int n, int k) {
     size_t b = gemm_workspace_bytes(M, n, k, 0, 0);
@@ -331,6 +339,179 @@ static int llm_stream_segment(const bd_llm_weights_t& w, int li, bool first, voi
   return stream_launch(prog, st);
 }
 
+// The whole AR block as ONE persistent launch (bd_stream.cuh): program iterations = decoder layers, per-layer weight
+// pointers from the device table w.layer_tab.
+//   pre : RMSNorm(ln1[0]) -> blocked a;  qkv GEMM of layer 0
+//   body (layer l): q/k norm + RoPE + KV append | paged attention (split-KV partials) | combine -> blocked o |
+//         o_proj (k-split partials) | residual + RMSNorm(ln2[l]) | gate/up GEMM (SwiGLU epilogue) | down (k-split partials) |
+//         residual + RMSNorm(ln1[l+1]) | qkv GEMM of layer l+1          (the last two skipped in the last layer)
+//   post: residual + final RMSNorm (+ pos-embed rows) -> out fp32
+static int llm_stream_all(const bd_llm_weights_t& w, void* hidden, int R, int S, const int* seq_lens, int sk_bound,
+                          void* kv_pool, int64_t kv_layer_stride, int64_t kv_v_offset, const int32_t* page_table,
+                          int max_pages, const float* rope_cos, const float* rope_sin, void* out, const float* out_add,
+                          int out_add_mod, uint8_t* base, const LlmWs& L, cudaStream_t st) {
+  const int M = R * S, D = w.D, G = w.stream_ctas, hd = w.head_dim, Ko = w.Hq * hd;
+  const int qkv_n = (w.Hq + 2 * w.Hkv) * hd;
+  BD_REQUIRE(w.n_layers <= kStreamMaxIter && S <= 64 && R * w.Hq <= 4096);
+  static thread_local StreamProgram prog;
+  prog = StreamProgram{};
+  prog.M = M;
+  prog.n_ctas = G;
+  prog.n_iter = w.n_layers;
+  prog.cfg_mult = 1;
+  prog.sync = reinterpret_cast<unsigned int*>(base + L.s_sync);
+  const void* const* tab = static_cast<const void* const*>(w.layer_tab);
+  enum { T_WQKV = 1, T_WO, T_WGU, T_WDOWN, T_LN1, T_LN2, T_QN, T_KN };  // slot + 1
+  // split of the key range: balance (units per CTA) x (key tiles per unit)
+  const int n_tiles = (sk_bound + 63) / 64;
+  int splits = 1;
+  {
+    double best = 1e30;
+    for (int s = 1; s <= kLlmMaxSplits && s <= n_tiles; ++s) {
+      const int rounds = (R * w.Hq * s + G - 1) / G;
+      const double cost = rounds * ((n_tiles + s - 1) / s + 1.0);
+      if (cost < best) {
+        best = cost;
+        splits = s;
+      }
+    }
+  }
+  float* part_o = reinterpret_cast<float*>(base + L.attn);
+  float* part_ml = part_o + static_cast<size_t>(splits) * R * w.Hq * S * hd;
+  __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(base + L.qkv);
+  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(base + L.q);
+  const int ks_o = stream_ksplit_for(D, Ko, G), ks_d = stream_ksplit_for(D, w.I, G);
+  int n = 0;
+  auto new_op = [&](int kind) -> StreamOp& {
+    StreamOp& op = prog.ops[n++];
+    op = StreamOp{};
+    op.kind = kind;
+    op.wait_prev = 1;
+    op.tab = tab;
+    return op;
+  };
+  auto gemm_op = [&](int tslot, int toff, const void* A, int N, int K, int ksplit, int epi, void* o, long long ld,
+                     bool blocked) -> StreamOp& {
+    StreamOp& op = new_op(kOpGemm);
+    op.sub = epi;
+    op.N = N;
+    op.K = K;
+    op.ksplit = ksplit;
+    op.flags = blocked ? kFlagBlocked : 0;
+    op.tab_p0 = tslot;
+    op.tab_off = toff;
+    op.p1 = A;
+    op.o0 = o;
+    op.l0 = ld;
+    return op;
+  };
+  auto row = [&](int sub) -> StreamOp& {
+    StreamOp& op = new_op(kOpRow);
+    op.sub = sub;
+    op.N = D;
+    op.f0 = w.eps;
+    op.o1 = hidden;
+    return op;
+  };
+  // ---- pre ----
+  {
+    StreamOp& op = row(kRowLlmRms);
+    op.wait_prev = 0;
+    op.tab_p1 = T_LN1;
+    op.o0 = base + L.s_a;
+  }
+  gemm_op(T_WQKV, 0, base + L.s_a, qkv_n, D, 1, kEpiBias, qkv, qkv_n, false);
+  prog.n_pre = n;
+  // ---- one layer ----
+  {
+    StreamOp& op = new_op(kOpLlmRope);
+    op.p0 = qkv;
+    op.tab_p1 = T_QN;
+    op.tab_p2 = T_KN;
+    op.p3 = rope_cos;
+    op.p4 = rope_sin;
+    op.p5 = seq_lens;
+    op.p6 = page_table;
+    op.o0 = q;
+    op.o1 = kv_pool;
+    op.l0 = kv_layer_stride;
+    op.l1 = kv_v_offset;
+    op.sub = R;
+    op.i0 = S;
+    op.i1 = w.Hq;
+    op.i2 = w.Hkv;
+    op.N = max_pages;
+    op.K = hd;
+    op.f0 = w.eps;
+  }
+  {
+    StreamOp& op = new_op(kOpLlmAttn);
+    op.p0 = q;
+    op.p1 = seq_lens;
+    op.p2 = page_table;
+    op.p3 = kv_pool;
+    op.l0 = kv_layer_stride;
+    op.l1 = kv_v_offset;
+    op.o0 = part_o;
+    op.o1 = part_ml;
+    op.sub = R;
+    op.ksplit = splits;
+    op.i0 = S;
+    op.i1 = w.Hq;
+    op.i2 = w.Hkv;
+    op.N = max_pages;
+    op.K = hd;
+    op.f0 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
+  }
+  {
+    StreamOp& op = new_op(kOpRow);
+    op.sub = kRowLlmAttnCombine;
+    op.p0 = part_o;
+    op.p1 = part_ml;
+    op.i0 = splits;
+    op.i1 = w.Hq;
+    op.i2 = S;
+    op.N = Ko;
+    op.K = hd;
+    op.o0 = base + L.s_o;
+  }
+  gemm_op(T_WO, 0, base + L.s_o, D, Ko, ks_o, kEpiPartial, base + L.s_part, 0, false);
+  {
+    StreamOp& op = row(kRowLlmResRms);
+    op.p0 = base + L.s_part;
+    op.i0 = ks_o;
+    op.tab_p1 = T_LN2;
+    op.o0 = base + L.s_a;
+  }
+  gemm_op(T_WGU, 0, base + L.s_a, 2 * w.I, D, 1, kEpiSwiglu8, base + L.s_g, 0, true);
+  gemm_op(T_WDOWN, 0, base + L.s_g, D, w.I, ks_d, kEpiPartial, base + L.s_part, 0, false);
+  {
+    StreamOp& op = row(kRowLlmResRms);
+    op.p0 = base + L.s_part;
+    op.i0 = ks_d;
+    op.tab_p1 = T_LN1;
+    op.tab_off = 1;
+    op.o0 = base + L.s_a;
+    op.flags |= kFlagSkipLast;
+  }
+  gemm_op(T_WQKV, 1, base + L.s_a, qkv_n, D, 1, kEpiBias, qkv, qkv_n, false).flags |= kFlagSkipLast;
+  prog.n_body = n - prog.n_pre;
+  // ---- post ----
+  {
+    StreamOp& op = row(kRowLlmResRms);
+    op.tab = nullptr;
+    op.p0 = base + L.s_part;
+    op.i0 = ks_d;
+    op.p1 = w.final_norm_w;
+    op.i1 = 1;
+    op.o0 = out;
+    op.p3 = out_add;
+    op.i2 = out_add_mod > 0 ? out_add_mod : 1;
+  }
+  prog.n_post = 1;
+  return stream_launch(prog, st);
+}
+
 }  // namespace bd
 
 using namespace bd;
@@ -430,6 +611,12 @@ int bd_llm_forward(const bd_llm_weights_t* wp, void* hidden, int stream_f32, int
       D <= 6144 && (w.I % 64) == 0) {
     // blocked operands are read in whole 128-row x 64-column tiles: padding rows / columns must be finite
     BD_CUDA_TRY(cudaMemsetAsync(base + L.s_a, 0, L.s_sync - L.s_a, st));
+    if (w.layer_tab && S <= 64 && w.n_layers <= kStreamMaxIter) {
+      BD_TRY(llm_stream_all(w, hidden, R, S, seq_lens, sk_bound, kv_pool, kv_layer_stride, kv_v_offset, page_table, max_pages,
+                            rope_cos, rope_sin, out, out_add, out_add_mod, base, L, st));
+      BD_TRY(launch_k(bump_seq_lens_kernel, dim3(1), dim3(256), 0, st, false, seq_lens, R, S));
+      return BD_OK;
+    }
     BD_TRY(llm_stream_segment(w, 0, true, hidden, M, base, L, qkv, qkv_n, out, out_add, out_add_mod, st));
     for (int li = 0; li < w.n_layers; ++li) {
       const bd_llm_layer_t& lw = w.layers[li];

@@ -520,6 +520,43 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       }
       return;
     }
+    case kRowLlmAttnCombine: {
+      // token row r = (sequence b, position s): reduce the split-KV partials of every q head in split order (the arithmetic of
+      // bd_attn.cu::bd_attn_combine_kernel) -> bf16 -> blocked operand of o_proj. p0 partial O fp32 [splits][R][Hq][S][hd],
+      // p1 partial (max, sum) [splits][R][Hq][S][2], i0 = splits, i1 = Hq, i2 = S, K = hd, o0 = out blocked
+      if (r >= M) return;
+      const int HD = op.K, Hq = op.i1, S = op.i2, splits = op.i0, R = M / S;
+      const int b = r / S, sq = r % S;
+      const float* part_o = reinterpret_cast<const float*>(op.p0);
+      const float* part_ml = reinterpret_cast<const float*>(op.p1);
+      const long long rows = static_cast<long long>(R) * Hq * S;
+      uint8_t* out = reinterpret_cast<uint8_t*>(op.o0);
+      const int vph = HD / 8;
+      for (int v = tid; v < Hq * vph; v += 128) {
+        const int h = v / vph, d0 = (v % vph) * 8;
+        const long long row = (static_cast<long long>(b) * Hq + h) * S + sq;
+        float mx = -FLT_MAX;
+        for (int sp = 0; sp < splits; ++sp) mx = fmaxf(mx, __ldcg(part_ml + (sp * rows + row) * 2));
+        float l = 0.f, acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int sp = 0; sp < splits; ++sp) {
+          const float ms = __ldcg(part_ml + (sp * rows + row) * 2), ls = __ldcg(part_ml + (sp * rows + row) * 2 + 1);
+          const float wgt = (ls > 0.f) ? exp2f(ms - mx) : 0.f;
+          l += ls * wgt;
+          const float* o = part_o + (sp * rows + row) * HD + d0;
+          const float4 x0 = ldcg_f4(o), x1 = ldcg_f4(o + 4);
+          acc[0] += x0.x * wgt; acc[1] += x0.y * wgt; acc[2] += x0.z * wgt; acc[3] += x0.w * wgt;
+          acc[4] += x1.x * wgt; acc[5] += x1.y * wgt; acc[6] += x1.z * wgt; acc[7] += x1.w * wgt;
+        }
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = acc[j] * inv;
+        *reinterpret_cast<uint4*>(out + blk_off(r, h * HD + d0)) = f_to_bf16x8(y);
+      }
+      return;
+    }
     case kRowLlmRms:
     case kRowLlmResRms: {
       // Qwen3DecoderLayer on the fp32 residual stream of an AR block (transformers qwen3; oracle/llm.py stream_f32):
@@ -756,6 +793,278 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Qwen3 decoder ops inside the engine (one persistent launch per AR block: csrc/bd_llm.cu::llm_stream_all)
+// ---------------------------------------------------------------------------------------------------------------------
+// q/k RMSNorm over head_dim + RoPE in fp32 + KV append (the arithmetic of bd_llm.cu::qk_norm_rope_append_kernel<HD, true>;
+// transformers qwen3 Qwen3Attention.forward). One warp per (token, head); the 4 x G epilogue warps stride over the tasks.
+template <int HD>
+__device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int c, int G, int tid) {
+  constexpr int VPT = HD / 32;
+  const int S = op.i0, Hq = op.i1, Hkv = op.i2, heads = Hq + 2 * Hkv, max_pages = op.N;
+  const int M = op.i0 * op.sub;  // sub = number of sequences
+  const int warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(op.p0);
+  const __nv_bfloat16* qn_w = reinterpret_cast<const __nv_bfloat16*>(op.p1);
+  const __nv_bfloat16* kn_w = reinterpret_cast<const __nv_bfloat16*>(op.p2);
+  const float* rope_cos = reinterpret_cast<const float*>(op.p3);
+  const float* rope_sin = reinterpret_cast<const float*>(op.p4);
+  const int* seq_lens = reinterpret_cast<const int*>(op.p5);
+  const int* page_table = reinterpret_cast<const int*>(op.p6);
+  __nv_bfloat16* q_out = reinterpret_cast<__nv_bfloat16*>(op.o0);
+  __nv_bfloat16* kpool = reinterpret_cast<__nv_bfloat16*>(op.o1) + static_cast<long long>(it) * op.l0;
+  __nv_bfloat16* vpool = kpool + op.l1;
+  const long long tasks = static_cast<long long>(M) * heads;
+  for (long long gw = static_cast<long long>(c) * 4 + warp; gw < tasks; gw += static_cast<long long>(G) * 4) {
+    const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
+    const int b = m / S, s = m % S;
+    const int pos = __ldcg(seq_lens + b) + s;
+    if (pos < 0 || pos >= max_pages * 64) {
+      if (lane == 0) printf("bd_stream: sequence %d position %d outside the KV cache (%d tokens)\n", b, pos, max_pages * 64);
+      __trap();
+    }
+    const __nv_bfloat16* src = qkv + static_cast<long long>(m) * heads * HD + static_cast<long long>(hh) * HD + lane * VPT;
+    float x[VPT];
+    if constexpr (VPT == 4) {
+      const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(src));
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const float2 a = __bfloat1622float2(p2[0]), bb = __bfloat1622float2(p2[1]);
+      x[0] = a.x; x[1] = a.y; x[2] = bb.x; x[3] = bb.y;
+    } else {
+      const uint32_t raw = __ldcg(reinterpret_cast<const uint32_t*>(src));
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
+      x[0] = a.x; x[1] = a.y;
+    }
+    const bool is_q = hh < Hq, is_k = !is_q && hh < Hq + Hkv;
+    __nv_bfloat16* dst;
+    if (is_q) {
+      dst = q_out + static_cast<long long>(m) * Hq * HD + static_cast<long long>(hh) * HD;
+    } else {
+      const int hk = is_k ? hh - Hq : hh - Hq - Hkv;
+      const int page = page_table[b * max_pages + pos / 64];
+      dst = (is_k ? kpool : vpool) + ((static_cast<long long>(page) * Hkv + hk) * 64 + (pos % 64)) * HD;
+    }
+    float y[VPT];
+    if (!is_q && !is_k) {  // V: plain copy
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) y[j] = x[j];
+    } else {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) ss += x[j] * x[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss / static_cast<float>(HD) + op.f0);
+      const __nv_bfloat16* nw = is_q ? qn_w : kn_w;
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) x[j] = bf16_round(__bfloat162float(nw[lane * VPT + j]) * bf16_round(x[j] * rstd));
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        const float other = __shfl_xor_sync(0xffffffffu, x[j], 16);
+        const float rot = (lane < 16) ? -other : other;  // rotate_half: cat(-x2, x1)
+        const int d = lane * VPT + j;
+        const float cs = rope_cos[static_cast<long long>(pos) * HD + d], sn = rope_sin[static_cast<long long>(pos) * HD + d];
+        y[j] = __fadd_rn(__fmul_rn(x[j], cs), __fmul_rn(rot, sn));
+      }
+    }
+    if constexpr (VPT == 4) {
+      uint2 pk;
+      __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]), bb = __floats2bfloat162_rn(y[2], y[3]);
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&bb);
+      *reinterpret_cast<uint2*>(dst + lane * VPT) = pk;
+    } else {
+      __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]);
+      *reinterpret_cast<uint32_t*>(dst + lane * VPT) = *reinterpret_cast<uint32_t*>(&a);
+    }
+  }
+}
+
+// 16-byte async copies (LDGSTS): the K / V tiles of the NEXT key tile land in shared memory while the current one is used
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;  // src-size 0 = zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// A 64-row tile of HD bf16 per row in shared memory, 16-byte chunks XOR-swizzled by (row & 7): conflict-free ldmatrix
+template <int HD>
+__device__ __forceinline__ uint32_t ltile_off(int row, int chunk) {
+  return static_cast<uint32_t>(row * (HD * 2) + ((chunk ^ (row & 7)) << 4));
+}
+template <int HD>
+__device__ __forceinline__ void ltile_load_async(uint8_t* tile, const __nv_bfloat16* src, long long row_stride, int valid_rows,
+                                                 int tid) {
+  constexpr int kChunks = HD / 8;
+  for (int i = tid; i < 64 * kChunks; i += 128) {
+    const int r = i / kChunks, ch = i % kChunks;
+    const bool ok = r < valid_rows;
+    cp_async16(tile + ltile_off<HD>(r, ch), src + (ok ? r : 0) * row_stride + ch * 8, ok);
+  }
+}
+
+// Flash attention of the block's S <= 64 query rows of one (sequence, q head) over a range of 64-key pages of the paged
+// cache (GQA: kv head = q head / (Hq / Hkv)); fp32 scores and softmax, P and the partial O in bf16 / fp32 like
+// bd_attn.cu. Units (split, sequence, head) are dealt round-robin to the CTAs; every unit writes its unnormalised partial
+// (O, max, sum) — the combine row op reduces the splits in a fixed order. K and V tiles are prefetched with cp.async while
+// the previous tile is in the tensor cores (mma.sync m16n8k16: this op is ~3 % of the block's time).
+template <int HD>
+__device__ __forceinline__ void llm_attn_units(const StreamOp& op, int it, int c, int G, int tid, uint8_t* smem) {
+  const int R = op.sub, S = op.i0, Hq = op.i1, Hkv = op.i2, splits = op.ksplit, max_pages = op.N;
+  const int units = R * Hq * splits;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 64 * HD * 2;
+  uint8_t* sV = sK + 64 * HD * 2;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(op.p0);
+  const int* seq_lens = reinterpret_cast<const int*>(op.p1);
+  const int* page_table = reinterpret_cast<const int*>(op.p2);
+  const __nv_bfloat16* kpool = reinterpret_cast<const __nv_bfloat16*>(op.p3) + static_cast<long long>(it) * op.l0;
+  const __nv_bfloat16* vpool = kpool + op.l1;
+  float* part_o = reinterpret_cast<float*>(op.o0);
+  float* part_ml = reinterpret_cast<float*>(op.o1);
+  const float scale_log2 = op.f0;
+  for (int u = c; u < units; u += G) {
+    const int h = u % Hq, b = (u / Hq) % R, split = u / (Hq * R);
+    const int hk = h / (Hq / Hkv);
+    const int Sk = __ldcg(seq_lens + b) + S;
+    const int n_tiles = (Sk + 63) / 64;
+    const int t_begin = static_cast<int>((static_cast<long long>(split) * n_tiles) / splits);
+    const int t_end = static_cast<int>((static_cast<long long>(split + 1) * n_tiles) / splits);
+    float o_acc[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
+    float m_run[2] = {-FLT_MAX, -FLT_MAX}, l_run[2] = {0.f, 0.f};
+    auto kv_src = [&](const __nv_bfloat16* pool, int kt) {
+      const int page = page_table[b * max_pages + kt];
+      return pool + (static_cast<long long>(page) * Hkv + hk) * 64 * HD;
+    };
+    epi_bar();  // the previous unit's tiles are dead
+    if (t_begin < t_end) {
+      ltile_load_async<HD>(sQ, q + (static_cast<long long>(b) * S) * Hq * HD + static_cast<long long>(h) * HD,
+                           static_cast<long long>(Hq) * HD, S, tid);
+      ltile_load_async<HD>(sK, kv_src(kpool, t_begin), HD, min(64, Sk - t_begin * 64), tid);
+      cp_async_commit();
+      ltile_load_async<HD>(sV, kv_src(vpool, t_begin), HD, min(64, Sk - t_begin * 64), tid);
+      cp_async_commit();
+    }
+    for (int kt = t_begin; kt < t_end; ++kt) {
+      const int k0 = kt * 64;
+      cp_async_wait<1>();  // Q + K(kt) landed (V(kt) may still be in flight)
+      epi_bar();
+      float sc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ks += 2) {
+        uint32_t a0[4], a1[4];
+        s_ldmatrix_x4(a0, smem_u32(sQ + ltile_off<HD>(warp * 16 + (lane & 15), 2 * ks + (lane >> 4))));
+        s_ldmatrix_x4(a1, smem_u32(sQ + ltile_off<HD>(warp * 16 + (lane & 15), 2 * ks + 2 + (lane >> 4))));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t bk[4];
+          s_ldmatrix_x4(bk, smem_u32(sK + ltile_off<HD>(8 * j + (lane & 7), 2 * ks + (lane >> 3))));
+          s_mma_16816(sc[j], a0, bk[0], bk[1]);
+          s_mma_16816(sc[j], a1, bk[2], bk[3]);
+        }
+      }
+      epi_bar();  // every warp is done with K(kt): fetch K(kt + 1) behind the softmax and P V of this tile
+      if (kt + 1 < t_end) ltile_load_async<HD>(sK, kv_src(kpool, kt + 1), HD, min(64, Sk - (kt + 1) * 64), tid);
+      cp_async_commit();
+      float m_new[2] = {m_run[0], m_run[1]};
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int key = k0 + 8 * j + 2 * t + (i & 1);
+          const float v = key < Sk ? sc[j][i] * scale_log2 : -FLT_MAX;
+          sc[j][i] = v;
+          m_new[i >> 1] = fmaxf(m_new[i >> 1], v);
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
+        m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
+      }
+      float corr[2], l_add[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) corr[r] = exp2f(m_run[r] - m_new[r]);
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          e[i] = (sc[j][i] == -FLT_MAX) ? 0.f : exp2f(sc[j][i] - m_new[i >> 1]);
+          l_add[i >> 1] += e[i];
+        }
+        const int kk = j >> 1;
+        if ((j & 1) == 0) {
+          pa[kk][0] = s_pack_bf16(e[0], e[1]);
+          pa[kk][1] = s_pack_bf16(e[2], e[3]);
+        } else {
+          pa[kk][2] = s_pack_bf16(e[0], e[1]);
+          pa[kk][3] = s_pack_bf16(e[2], e[3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        l_run[r] = l_run[r] * corr[r] + l_add[r];
+        m_run[r] = m_new[r];
+      }
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n) {
+        o_acc[n][0] *= corr[0];
+        o_acc[n][1] *= corr[0];
+        o_acc[n][2] *= corr[1];
+        o_acc[n][3] *= corr[1];
+      }
+      cp_async_wait<1>();  // V(kt) landed (K(kt + 1) may still be in flight)
+      epi_bar();
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int n = 0; n < HD / 8; n += 2) {
+          uint32_t bv[4];
+          s_ldmatrix_x4_trans(bv, smem_u32(sV + ltile_off<HD>(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), n + (lane >> 4))));
+          s_mma_16816(o_acc[n], pa[kk], bv[0], bv[1]);
+          s_mma_16816(o_acc[n + 1], pa[kk], bv[2], bv[3]);
+        }
+      }
+      epi_bar();  // every warp is done with V(kt)
+      if (kt + 1 < t_end) ltile_load_async<HD>(sV, kv_src(vpool, kt + 1), HD, min(64, Sk - (kt + 1) * 64), tid);
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qrow = warp * 16 + g + 8 * r;
+      if (qrow >= S) continue;
+      const long long row = ((static_cast<long long>(split) * R + b) * Hq + h) * S + qrow;
+      float* o = part_o + row * HD;
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n)
+        *reinterpret_cast<float2*>(o + 8 * n + 2 * t) = make_float2(o_acc[n][2 * r], o_acc[n][2 * r + 1]);
+      if (t == 0) {
+        part_ml[row * 2] = m_run[r];
+        part_ml[row * 2 + 1] = l_run[r];
+      }
+    }
+  }
+  epi_bar();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kAccBufs = 3;            // TMEM accumulator buffers: 0 / 1 alternate over the passes of the dependent chain,
@@ -765,6 +1074,7 @@ struct StreamSmem {
   static constexpr int kRing = kStreamSlots * kStepBytes;
   // rings, accumulators, the epilogue warps' own bulk-copy barrier, + the scratch handshake (A ring lent to an executor)
   static constexpr int kBars = (2 * kStreamSlots + 2 * kAccBufs + 1 + 2) * 8;
+  static constexpr int kTmemSlotOff = 192, kRedOff = 200;
   static constexpr int kBias = kAccBufs * 512;  // one pass's bias slice (<= 128 values, fp32) per accumulator buffer
   static constexpr int kMisc = 256;      // barriers (<= 168 B), TMEM slot at +192, reduction scratch at +208
   static_assert(kBars <= 192, "barrier area");
@@ -847,6 +1157,11 @@ __device__ __forceinline__ bool op_skipped(const StreamProgram& prog, const Stre
   return (op.flags & kFlagSkipLast) && it == prog.n_iter - 1;
 }
 
+__device__ __forceinline__ const void* tab_ptr(const StreamOp& op, int it, int slot1, const void* dflt) {
+  if (!op.tab || slot1 == 0) return dflt;
+  return op.tab[static_cast<long long>(it + op.tab_off) * kTabSlots + (slot1 - 1)];
+}
+
 // The attention executor and the final-row executor borrow the A ring as scratch. Without fillers nothing can be in flight
 // there (the A producer is parked at the next GEMM's grid barrier); with fillers — GEMM work without dependencies — the A
 // producer could be streaming a piece's operand into the ring at that very moment (always in a CTA that has no share of
@@ -854,6 +1169,7 @@ __device__ __forceinline__ bool op_skipped(const StreamProgram& prog, const Stre
 // scr_free, and resumes only after the executors signal scr_done.
 __device__ __forceinline__ bool op_uses_scratch(const StreamProgram& prog, const StreamOp& op, int c) {
   if (op.kind == kOpAttn) return c < (prog.M / op.i0) * (op.N / op.K);
+  if (op.kind == kOpLlmAttn) return c < op.sub * op.i1 * op.ksplit;
   return op.kind == kOpRow && op.sub == kRowFinal && c < prog.M;
 }
 
@@ -880,13 +1196,13 @@ struct WStream {
       if (!gw.any()) continue;
       part = gw.part;
       N = op.N;
-      w = reinterpret_cast<const uint8_t*>(op.p0);
+      w = reinterpret_cast<const uint8_t*>(tab_ptr(op, it, op.tab_p0, op.p0));
       i = gw.p0;
       pass_end = gw.p1;
       kb_first = gw.kb_first;
       kbn = gw.kbn;
       nsteps = stream_steps(kbn);
-      rot = stream_k_rot(c, nsteps);
+      rot = stream_k_rot(c, nsteps, prog.dbg_mode);
       t = 0;
       set_pass();
       return true;
@@ -1037,7 +1353,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         }
         BD_STAMP(cur.q, 0);
         const int nsteps = stream_steps(gw.kbn);
-        const int rot = stream_k_rot(c, nsteps);
+        const int rot = stream_k_rot(c, nsteps, prog.dbg_mode);
         const uint8_t* abase = reinterpret_cast<const uint8_t*>(op.p1);
         if (op.flags & kFlagAPerIt) abase += static_cast<long long>(cur.it + op.i0) * ((op.K + 63) / 64) * kSlotBytes;
         abase += static_cast<long long>(gw.part.kb0 + gw.kb_first) * kSlotBytes;
@@ -1082,7 +1398,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * 128u;
           const int nsteps = stream_steps(gw.kbn);
-          const int rot = stream_k_rot(c, nsteps);
+          const int rot = stream_k_rot(c, nsteps, prog.dbg_mode);
           const uint32_t kb_bytes = static_cast<uint32_t>(w) * 128u;
           const uint32_t keep = gw.first ? 0u : 1u;  // later pieces of a pass accumulate onto the earlier ones
           for (int t = 0; t < nsteps; ++t) {
@@ -1133,6 +1449,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
       // by value: the descriptor lives in registers for the whole op. (Reading it through the kernel-parameter bank with a
       // run-time index inside the per-element epilogue loops cost ~3 us per 32-column chunk: measured 11 us -> 1 us.)
       StreamOp op = prog.ops[cur.idx];
+      if (op.tab) {
+        op.p0 = tab_ptr(op, it, op.tab_p0, op.p0);
+        op.p1 = tab_ptr(op, it, op.tab_p1, op.p1);
+        op.p2 = tab_ptr(op, it, op.tab_p2, op.p2);
+      }
       const bool skipped = op_skipped(prog, op, it);
       const bool filler = (op.flags & kFlagFiller) != 0;
       if ((op.flags & kFlagParityIt) ? (it & 1) : ((op.flags & kFlagParityNext) ? ((it + 1) & 1) : 0)) {
@@ -1223,6 +1544,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         if (scratch) mbar_wait(scr_free, scr_uses & 1u);  // the A ring is ours (see op_uses_scratch)
         if (op.kind == kOpRow) {
           row_op(prog, op, it, c, tid, red, smem_a);
+        } else if (op.kind == kOpLlmRope) {
+          if (op.K == 128) llm_rope_append<128>(op, it, c, G, tid);
+          else llm_rope_append<64>(op, it, c, G, tid);
+        } else if (op.kind == kOpLlmAttn) {
+          if (op.K == 128) llm_attn_units<128>(op, it, c, G, tid, smem_a);
+          else llm_attn_units<64>(op, it, c, G, tid, smem_a);
         } else {
           const int units = (prog.M / op.i0) * (op.N / op.K);
           if (c < units) {

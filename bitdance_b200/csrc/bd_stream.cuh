@@ -34,10 +34,14 @@ constexpr int kStepBytes = kKbPerStep * kSlotBytes;
 constexpr int kStreamSlots = 7;          // shared-memory ring slots (32 KB each) in total (W ring + A ring)
 constexpr int kStreamWSlotsDefault = 5;
 constexpr int kStreamASlotsDefault = 2;
-constexpr int kStreamMaxOps = 160;  // the program travels as a kernel parameter (< 32 KB)
+constexpr int kStreamMaxOps = 128;  // the program travels as a kernel parameter (< 32 KB)
 constexpr int kStreamMaxIter = 104;
 
-enum : int { kOpGemm = 0, kOpRow = 1, kOpAttn = 2 };
+enum : int {
+  kOpGemm = 0, kOpRow = 1, kOpAttn = 2,
+  kOpLlmRope = 3,   // Qwen3: q/k RMSNorm over head_dim + RoPE (fp32) + paged KV append, one warp per (token, head)
+  kOpLlmAttn = 4,   // Qwen3: flash attention of the block's queries over the paged cache, split-KV partials
+};
 enum : int {
   kFlagBlocked = 1, kFlagParityIt = 2, kFlagParityNext = 4, kFlagSkipLast = 8,
   kFlagFiller = 16,   // GEMM op outside the grid-barrier sequence (see "fillers" below)
@@ -57,6 +61,7 @@ enum : int {
   kRowLlmRms = 8,     // Qwen3 RMSNorm of an fp32 residual row -> blocked bf16
   kRowLlmResRms = 9,  // residual += bf16(sum partials); then RMSNorm -> blocked bf16, or the final norm (+ pos table) -> fp32
   kRowSiluAddAll = 10,// kRowSiluAdd for EVERY iteration at once: y[it] = silu(temb[it] + cemb[r]) -> o0 + it * l1 (blocked)
+  kRowLlmAttnCombine = 11,  // fixed-order combine of the split-KV attention partials of token row r -> blocked bf16 operand
 };
 
 // One op. Field meaning per kind:
@@ -76,6 +81,16 @@ enum : int {
 //        stream stay busy while the epilogue warps run the row op / wait for the grid barrier. Because the A ring doubles
 //        as scratch of the attention / final-row executors, a filler must never sit between a GEMM and such an op in GEMM
 //        order (the host program builder guarantees it).
+//  PER-ITERATION POINTERS (tab != nullptr): a body op of a program whose iterations are the LAYERS of a decoder takes its
+//        weight pointers from a device table tab[(it + tab_off) * kTabSlots + slot]; tab_p0 / tab_p1 / tab_p2 = slot + 1 of
+//        the table entry that replaces p0 / p1 / p2 (0: keep the field).
+//  LLM_ROPE: p0 = qkv row-major bf16 [M, (Hq + 2 Hkv) hd], p1 / p2 = q_norm / k_norm weights bf16 [hd], p3 / p4 = RoPE cos /
+//        sin fp32 [pos, hd], p5 = seq_lens int32 [R], p6 = page_table int32 [R, N], o0 = q out row-major bf16 [M, Hq hd],
+//        o1 = K pool of layer 0 (layer `it` at + it * l0 elements, V pool at + l1 elements; pools [page][Hkv][64][hd]),
+//        i0 = S tokens per sequence, i1 = Hq, i2 = Hkv, N = max_pages, K = hd, f0 = eps
+//  LLM_ATTN: p0 = q (as above), p1 = seq_lens, p2 = page_table, p3 = K pool of layer 0 (l0, l1 as above), o0 = partial O fp32
+//        [ksplit][R][Hq][S][hd] (unnormalised), o1 = partial (max, sum) fp32 [ksplit][R][Hq][S][2], sub = R, ksplit = splits of
+//        the key range, i0 = S, i1 = Hq, i2 = Hkv, N = max_pages, K = hd, f0 = softmax scale * log2(e)
 //  ROW:  sub = row kind; pointers documented at each row function
 //  ATTN: p0 = qkv row-major bf16 [M, 3D], o0 = out blocked bf16, N = D, K = head_dim
 struct StreamOp {
@@ -96,7 +111,10 @@ struct StreamOp {
   float f0;
   int i0, i1, i2;
   int pc_pass, pc_kb0, pc_kbn, pc_flags;  // piece of a GEMM (pc_kbn > 0), see FILLERS
+  const void* const* tab;                 // per-iteration pointer table (device), see PER-ITERATION POINTERS
+  int tab_p0, tab_p1, tab_p2, tab_off;
 };
+constexpr int kTabSlots = 8;
 
 struct StreamProgram {
   int n_pre, n_body, n_iter, n_post;
@@ -166,7 +184,13 @@ __host__ __device__ inline long long stream_pass_offset(int N, const StreamPart&
 // the K loop advances in steps of kKbPerStep k-blocks (the last step may be short); rotation: CTAs start at different
 // steps so that they do not all hit the same L2 lines of A at once
 __host__ __device__ inline int stream_steps(int kbs) { return (kbs + kKbPerStep - 1) / kKbPerStep; }
-__host__ __device__ inline int stream_k_rot(int c, int nsteps) { return (c * 3) % nsteps; }
+// mode (bd_stream_set_tuning, measurement): bit 3 = no rotation (every CTA walks K in the same order: the L2 sees ~148
+// requests for the same lines within a short window); bit 4 = CTAs rotate in groups of 4 (4 requesters per line)
+__host__ __device__ inline int stream_k_rot(int c, int nsteps, int mode = 0) {
+  if (mode & 8) return 0;
+  if (mode & 16) return ((c >> 2) * 3) % nsteps;
+  return (c * 3) % nsteps;
+}
 
 // byte offset of element (row, col) inside a blocked bf16 activation [K/64][128][64] with the 128-byte swizzle
 __host__ __device__ inline long long blk_off(int row, int col) {

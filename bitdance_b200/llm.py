@@ -25,7 +25,8 @@ class LlmLayer(C.Structure):
 class LlmWeights(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("D", "I", "n_layers", "Hq", "Hkv", "head_dim")] + [
         ("eps", C.c_float), ("w_tiled", C.c_int), ("stream_ctas", C.c_int), ("variant", C.c_int),
-        ("final_norm_w", C.c_void_p), ("layers", C.POINTER(LlmLayer)), ("emb_norm_w", C.c_void_p)]
+        ("final_norm_w", C.c_void_p), ("layers", C.POINTER(LlmLayer)), ("emb_norm_w", C.c_void_p),
+        ("layer_tab", C.c_void_p)]
 
 ROPE_PAIRS = 1  # BD_LLM_ROPE_PAIRS (include/bitdance_b200.h)
 
@@ -151,6 +152,13 @@ class LlmRunner:
         w.stream_ctas = n_ctas
         w.final_norm_w = fn.data_ptr()
         w.variant = ROPE_PAIRS if rope_pairs is not None else 0
+        if n_ctas and qk_norm:
+            # per-layer pointer table of the one-launch AR block (bd_llm_weights_t.layer_tab): [L + 1][8]
+            rows = [[lw.wqkv_s, lw.wo_s, lw.w_gate_up_s, lw.w_down_s, lw.ln1_w, lw.ln2_w, lw.q_norm_w, lw.k_norm_w]
+                    for lw in layers] + [[0] * 8]
+            tab = torch.tensor([[int(v or 0) for v in r] for r in rows], dtype=torch.int64).to(dev)
+            self._keep.append(tab)
+            w.layer_tab = tab.data_ptr()
         if emb_norm is not None:
             en = emb_norm.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
             self._keep.append(en)

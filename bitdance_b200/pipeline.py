@@ -82,6 +82,18 @@ class T2IEngine:
         c.host_lens = [0] * R
         return c
 
+    def weight_tensors(self):
+        """Every prepacked weight tensor the engine streams (decoder, head, projector, tokenizer) — the set a start-up
+        ``parallel.broadcast_tensors`` ships from rank 0 instead of N disk reads."""
+        ts = [t for t in self.llm._keep if t is not None] + [t for t in self.head._keep if t is not None]
+        ts += [self.fc1_w.data, self.fc1_b, self.fc2_w.data, self.fc2_b]
+        if self.ae is not None:
+            for c in self.ae.convs.values():
+                ts += [c.w] + ([c.b] if c.b is not None else [])
+            for a, b in list(self.ae.norms.values()) + list(self.ae.ada.values()):
+                ts += [a, b]
+        return ts
+
     def pos_embed(self, h, w):
         if (h, w) not in self._pos_cache:
             self._pos_cache[(h, w)] = pos_embed_2d(self.pos_1d, h, w, self.ps)

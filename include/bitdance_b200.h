@@ -222,6 +222,11 @@ typedef struct {
   const bd_llm_layer_t* layers; /* HOST array [n_layers] */
   const void* emb_norm_w;       /* bf16 [D] or NULL: RMSNorm applied to the input embeddings in place before the first
                                  * layer (BitDance.forward_model, imagenet_gen/src/model_parallel.py:343-345) */
+  const void* layer_tab;        /* DEVICE table of pointers [n_layers + 1][8] (the last row unused): {wqkv_s, wo_s,
+                                 * w_gate_up_s, w_down_s, ln1_w, ln2_w, q_norm_w, k_norm_w} of every layer, or NULL. With it
+                                 * (and stream_ctas > 0) an fp32-stream, non-causal pass of R*S <= 128 rows runs as ONE
+                                 * persistent launch: all layers' Linears, norms, RoPE + KV append, paged attention and its
+                                 * split-KV combine are ops of bd_stream_kernel (csrc/bd_llm.cu::llm_stream_all) */
 } bd_llm_weights_t;
 #define BD_LLM_ROPE_PAIRS 1
 

@@ -12,6 +12,9 @@ for step in "$@"; do
     head)     timeout 900 python -m pytest tests/test_head_gpu.py -m gpu -q -s 2>&1 | grep -v "^    \|^$" | tail -150 > gpurun_out/${TAG}_test_head.log ;;
     head0)    BD_HEAD_FILLERS=0 timeout 900 python -m pytest tests/test_head_gpu.py -m gpu -q -s -k "stream" 2>&1 | grep -v "^    \|^$" | tail -150 > gpurun_out/${TAG}_test_head_fill0.log ;;
     tests)    timeout 2400 python -m pytest tests -m gpu -q -s 2>&1 | grep -v "^    " > gpurun_out/${TAG}_tests.log ;;
+    llmstream) BD_LLM_STREAM=1 timeout 900 python -m pytest tests/test_llm_gpu.py tests/test_pipeline_gpu.py -m gpu -q -s 2>&1 | grep -v "^    " | tail -80 > gpurun_out/${TAG}_test_llm_stream.log ;;
+    benchllm) BD_LLM_STREAM=1 timeout 1500 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_llmstream.json 2> gpurun_out/${TAG}_bench_llmstream.err ;;
+    benchquick) timeout 1500 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_quick.json 2> gpurun_out/${TAG}_bench_quick.err ;;
     timeline) timeout 900 python scripts/head_timeline.py > gpurun_out/${TAG}_head_timeline.txt 2>&1 ;;
     ab)       timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab.txt 2>&1 ;;
     ab_r01)   BD_LIB_PATH=$PWD/ab/libbitdance_b200_r01.so timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab_r01.txt 2>&1 ;;

@@ -37,10 +37,13 @@ def smi():
 
 
 def set_mode(m):
+    """mode = fill[:row_kb[:gemm_kb[:tuning[:w_slots]]]] (tuning = bd_stream_set_tuning mode bits, e.g. 8 = no K rotation)"""
     if m == "lib":
         return
-    f = [int(x) for x in m.split(":")] + [0, 0]
+    f = [int(x) for x in m.split(":")] + [0, 0, 0, 0]
     lib.bd_head_set_fillers(f[0], f[1] or 22, f[2] or 8)
+    w_slots = f[4] or 5
+    lib.bd_stream_set_tuning(w_slots, 7 - w_slots, f[3])
 
 
 res = {m: [] for m in modes}
