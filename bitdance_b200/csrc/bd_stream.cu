@@ -364,6 +364,119 @@ __device__ __forceinline__ void row_op_ln_family(const StreamProgram& prog, cons
   epi_bar();  // arow (aliasing the A ring) is dead before anything else may touch it
 }
 
+// Qwen3 residual add + RMSNorm of token row r with the loads of every phase issued together (see the note at the top of
+// the row ops). Field meaning: kRowLlmRms / kRowLlmResRms in row_op.
+template <int NV>
+__device__ __forceinline__ void llm_res_rms(const StreamOp& op, int M, int r, int tid, float* red) {
+  const int D = op.N, nvec = D / 8;
+  float* hid = reinterpret_cast<float*>(op.o1) + static_cast<long long>(r) * D;
+  float v[NV][8];
+  if (op.sub == kRowLlmResRms) {
+    const float* part = reinterpret_cast<const float*>(op.p0) + static_cast<long long>(r) * D;
+    const long long sstride = static_cast<long long>(M) * D;
+    float acc[NV][8];
+    auto add_split = [&](int s, bool first) {
+      float4 x0[NV], x1[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = tid + i * 128;
+        x0[i] = x1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nvec) {
+          const float* q = part + s * sstride + c * 8;
+          x0[i] = ldcg_f4(q);
+          x1[i] = ldcg_f4(q + 4);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (first) {
+          acc[i][0] = x0[i].x; acc[i][1] = x0[i].y; acc[i][2] = x0[i].z; acc[i][3] = x0[i].w;
+          acc[i][4] = x1[i].x; acc[i][5] = x1[i].y; acc[i][6] = x1[i].z; acc[i][7] = x1[i].w;
+        } else {
+          acc[i][0] += x0[i].x; acc[i][1] += x0[i].y; acc[i][2] += x0[i].z; acc[i][3] += x0[i].w;
+          acc[i][4] += x1[i].x; acc[i][5] += x1[i].y; acc[i][6] += x1[i].z; acc[i][7] += x1[i].w;
+        }
+      }
+    };
+    add_split(0, true);  // fixed order: deterministic
+    for (int s = 1; s < op.i0; ++s) {
+      if ((s & 1) == 0) compiler_fence();
+      add_split(s, false);
+    }
+    compiler_fence();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = tid + i * 128;
+      if (c < nvec) {
+        const float4 r0 = ldcg_f4(hid + c * 8), r1 = ldcg_f4(hid + c * 8 + 4);
+        const float res[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = res[j] + bf16_round(acc[i][j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = tid + i * 128;
+      if (c < nvec) {
+        *reinterpret_cast<float4*>(hid + c * 8) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        *reinterpret_cast<float4*>(hid + c * 8 + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = tid + i * 128;
+      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+      if (c < nvec) {
+        r0 = ldcg_f4(hid + c * 8);
+        r1 = ldcg_f4(hid + c * 8 + 4);
+      }
+      v[i][0] = r0.x; v[i][1] = r0.y; v[i][2] = r0.z; v[i][3] = r0.w;
+      v[i][4] = r1.x; v[i][5] = r1.y; v[i][6] = r1.z; v[i][7] = r1.w;
+    }
+  }
+  if (!op.p1) return;
+  // norm weights (read-only): in flight during the reduction
+  uint4 nwr[NV];
+  const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(op.p1);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = tid + i * 128;
+    nwr[i] = c < nvec ? ldg_u4(nw + c * 8) : make_uint4(0, 0, 0, 0);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+  const float rstd = rsqrtf(epi_sum(ss, red, tid) / static_cast<float>(D) + op.f0);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = tid + i * 128;
+    if (c < nvec) {
+      float wv[8], y[8];
+      bf16x8_to_f(nwr[i], wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = wv[j] * (v[i][j] * rstd);
+      if (op.i1) {
+        float* o = reinterpret_cast<float*>(op.o0) + static_cast<long long>(r) * D + c * 8;
+        if (op.p3) {
+          const float* add = reinterpret_cast<const float*>(op.p3) + static_cast<long long>(r % op.i2) * D + c * 8;
+          const float4 a0 = ldg_f4(add), a1 = ldg_f4(add + 4);
+          y[0] += a0.x; y[1] += a0.y; y[2] += a0.z; y[3] += a0.w; y[4] += a1.x; y[5] += a1.y; y[6] += a1.z; y[7] += a1.w;
+        }
+        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      } else {
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(op.o0) + blk_off(r, c * 8)) = f_to_bf16x8(y);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp& op, int it, int r, int tid, float* red,
                                        uint8_t* scratch) {
   const int M = prog.M;
@@ -566,64 +679,8 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       // p0 partials fp32 [S][M][D] (i0 = S), o1 hidden fp32 [M, D] in/out, p1 norm weight bf16 [D] (nullable for i1 == 0: no
       // norm), p3 add table fp32 [i2][D] (nullable), o0 output
       if (r >= M) return;
-      const int D = op.N, nvec = D / 8;
-      float* hid = reinterpret_cast<float*>(op.o1) + static_cast<long long>(r) * D;
-      float v[kRowVec][8];
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < kRowVec; ++i) {
-        const int c = tid + i * 128;
-        if (c < nvec) {
-          const float4 r0 = ldcg_f4(hid + c * 8), r1 = ldcg_f4(hid + c * 8 + 4);
-          const float res[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          if (op.sub == kRowLlmResRms) {
-            const float* part = reinterpret_cast<const float*>(op.p0);
-            float acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-            for (int sp = 0; sp < op.i0; ++sp) {  // fixed order: deterministic
-              const float* q = part + (static_cast<long long>(sp) * M + r) * D + c * 8;
-              const float4 x0 = ldcg_f4(q), x1 = ldcg_f4(q + 4);
-              acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
-              acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[i][j] = res[j] + bf16_round(acc[j]);
-            *reinterpret_cast<float4*>(hid + c * 8) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
-            *reinterpret_cast<float4*>(hid + c * 8 + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[i][j] = res[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
-        }
-      }
-      if (!op.p1) return;
-      const float rstd = rsqrtf(epi_sum(ss, red, tid) / static_cast<float>(D) + op.f0);
-      const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(op.p1);
-#pragma unroll
-      for (int i = 0; i < kRowVec; ++i) {
-        const int c = tid + i * 128;
-        if (c < nvec) {
-          float wv[8], y[8];
-          bf16x8_to_f(*reinterpret_cast<const uint4*>(nw + c * 8), wv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = wv[j] * (v[i][j] * rstd);
-          if (op.i1) {
-            float* o = reinterpret_cast<float*>(op.o0) + static_cast<long long>(r) * D + c * 8;
-            if (op.p3) {
-              const float* add = reinterpret_cast<const float*>(op.p3) + static_cast<long long>(r % op.i2) * D + c * 8;
-              const float4 a0 = *reinterpret_cast<const float4*>(add), a1 = *reinterpret_cast<const float4*>(add + 4);
-              y[0] += a0.x; y[1] += a0.y; y[2] += a0.z; y[3] += a0.w; y[4] += a1.x; y[5] += a1.y; y[6] += a1.z; y[7] += a1.w;
-            }
-            *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
-          } else {
-            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(op.o0) + blk_off(r, c * 8)) = f_to_bf16x8(y);
-          }
-        }
-      }
+      if (op.N == 5120) llm_res_rms<5>(op, M, r, tid, red);
+      else llm_res_rms<kRowVec>(op, M, r, tid, red);
       return;
     }
     default: return;
