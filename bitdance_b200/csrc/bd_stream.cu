@@ -1132,10 +1132,14 @@ struct StreamSmem {
   // rings, accumulators, the epilogue warps' own bulk-copy barrier, + the scratch handshake (A ring lent to an executor)
   static constexpr int kBars = (2 * kStreamSlots + 2 * kAccBufs + 1 + 2) * 8;
   static constexpr int kTmemSlotOff = 192, kRedOff = 200;
-  static constexpr int kBias = kAccBufs * 512;  // one pass's bias slice (<= 128 values, fp32) per accumulator buffer
+  static constexpr int kBias = kAccBufs * kAccStride * 4;  // one pass's bias slice (<= 160 values, fp32) per accumulator buffer
   static constexpr int kMisc = 256;      // barriers (<= 168 B), TMEM slot at +192, reduction scratch at +208
   static_assert(kBars <= 192, "barrier area");
-  static constexpr int kTotal = kRing + kMisc + kBias + 1024 /*align slack*/;
+  // 227 KB is the most a CTA can have: 896 bytes are left for aligning the ring to 1024 (128B-swizzle atom). The dynamic
+  // shared-memory window of a kernel without static shared memory starts 1024-aligned; the kernel checks and traps otherwise.
+  static constexpr int kAlignSlack = 896;
+  static constexpr int kTotal = kRing + kMisc + kBias + kAlignSlack;
+  static_assert(kTotal <= 227 * 1024, "shared memory");
 };
 
 struct RingPos {  // position in a ring of n slots: slot index + how many times the ring wrapped
@@ -1236,7 +1240,7 @@ struct WStream {
   const StreamProgram& prog;
   int G, c, total;
   int q = -1, i = 0, t = 0;           // op sequence number, pass, step
-  int pass_end = 0, nsteps = 0, rot = 0, kbn = 0, kb_first = 0, N = 0;
+  int pass_end = 0, nsteps = 0, rot = 0, kbn = 0, kb_first = 0, N = 0, kps = kKbPerStep;
   StreamPart part{};
   const uint8_t* w = nullptr;
   const uint8_t* base = nullptr;      // first slot of the current pass
@@ -1258,8 +1262,6 @@ struct WStream {
       pass_end = gw.p1;
       kb_first = gw.kb_first;
       kbn = gw.kbn;
-      nsteps = stream_steps(kbn);
-      rot = stream_k_rot(c, nsteps, prog.dbg_mode);
       t = 0;
       set_pass();
       return true;
@@ -1270,6 +1272,9 @@ struct WStream {
     const int wd = (stream_pass_u0(part, i + 1) - stream_pass_u0(part, i)) * 16;
     kb_bytes = static_cast<uint32_t>(wd) * 128u;
     base = w + stream_pass_offset(N, part, i) * 2048;
+    kps = stream_kps(wd);
+    nsteps = stream_steps(kbn, kps);
+    rot = stream_k_rot(c, nsteps, prog.dbg_mode);
   }
   // address / size of the next step; false at the end of the program
   __device__ __forceinline__ bool next(const uint8_t*& addr, uint32_t& bytes) {
@@ -1284,8 +1289,8 @@ struct WStream {
     }
     int st = rot + t;
     if (st >= nsteps) st -= nsteps;
-    const int kbl = st * kKbPerStep;
-    const int nkb = min(kKbPerStep, kbn - kbl);
+    const int kbl = st * kps;
+    const int nkb = min(kps, kbn - kbl);
     bytes = kb_bytes * static_cast<uint32_t>(nkb);  // the k-blocks of a pass are adjacent in HBM
     addr = base + static_cast<long long>(kb_first + kbl) * kb_bytes;
     ++t;
@@ -1307,6 +1312,10 @@ __device__ __forceinline__ unsigned int wait_target(int wait_prev, unsigned int 
 __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __grid_constant__ StreamProgram prog) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0 && static_cast<int>(smem - smem_raw) > StreamSmem::kAlignSlack) {
+    printf("bd_stream: dynamic shared memory base %p is not aligned enough\n", static_cast<void*>(smem_raw));
+    __trap();
+  }
   const uint32_t kStreamWSlots = static_cast<uint32_t>(prog.w_slots), kStreamASlots = static_cast<uint32_t>(prog.a_slots);
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + kStreamWSlots * kStepBytes;
@@ -1409,17 +1418,18 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           fence_proxy_async_all();  // other CTAs' generic-proxy stores -> this thread's async-proxy (bulk copy) reads
         }
         BD_STAMP(cur.q, 0);
-        const int nsteps = stream_steps(gw.kbn);
-        const int rot = stream_k_rot(c, nsteps, prog.dbg_mode);
         const uint8_t* abase = reinterpret_cast<const uint8_t*>(op.p1);
         if (op.flags & kFlagAPerIt) abase += static_cast<long long>(cur.it + op.i0) * ((op.K + 63) / 64) * kSlotBytes;
         abase += static_cast<long long>(gw.part.kb0 + gw.kb_first) * kSlotBytes;
         for (int i = gw.p0; i < gw.p1; ++i) {
+          const int kps = stream_kps((stream_pass_u0(gw.part, i + 1) - stream_pass_u0(gw.part, i)) * 16);
+          const int nsteps = stream_steps(gw.kbn, kps);
+          const int rot = stream_k_rot(c, nsteps, prog.dbg_mode);
           for (int t = 0; t < nsteps; ++t) {
             int st = rot + t;
             if (st >= nsteps) st -= nsteps;
-            const int kbl = st * kKbPerStep;
-            const uint32_t bytes = static_cast<uint32_t>(min(kKbPerStep, gw.kbn - kbl)) * kSlotBytes;
+            const int kbl = st * kps;
+            const uint32_t bytes = static_cast<uint32_t>(min(kps, gw.kbn - kbl)) * kSlotBytes;
             const uint32_t s = ar.slot;
             if (ar.round > 0) mbar_wait(&empty_a[s], (ar.round & 1u) ^ 1u);
             mbar_expect_tx(&full_a[s], bytes);
@@ -1453,15 +1463,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
             mbar_wait(&acc_empty[buf], ((pi >> 1) & 1u) ^ 1u);
           }
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * 128u;
-          const int nsteps = stream_steps(gw.kbn);
+          const uint32_t d_tmem = tmem_base + buf * static_cast<uint32_t>(kAccStride);
+          const int kps = stream_kps(w);
+          const int nsteps = stream_steps(gw.kbn, kps);
           const int rot = stream_k_rot(c, nsteps, prog.dbg_mode);
           const uint32_t kb_bytes = static_cast<uint32_t>(w) * 128u;
           const uint32_t keep = gw.first ? 0u : 1u;  // later pieces of a pass accumulate onto the earlier ones
           for (int t = 0; t < nsteps; ++t) {
             int st = rot + t;
             if (st >= nsteps) st -= nsteps;
-            const int nkb = min(kKbPerStep, gw.kbn - st * kKbPerStep);
+            const int nkb = min(kps, gw.kbn - st * kps);
             const uint32_t sw = wr.slot, sa = ar.slot;
             mbar_wait(&full_w[sw], wr.round & 1u);
             mbar_wait(&full_a[sa], ar.round & 1u);
@@ -1547,17 +1558,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
             if (tid < w / 8) {
               float t8[8];
               bf16x8_to_f(ldg_u4(reinterpret_cast<const __nv_bfloat16*>(op.p2) + n0 + tid * 8), t8);
-              float4* dst4 = reinterpret_cast<float4*>(bias_s + buf * 128 + tid * 8);
+              float4* dst4 = reinterpret_cast<float4*>(bias_s + buf * kAccStride + tid * 8);
               dst4[0] = make_float4(t8[0], t8[1], t8[2], t8[3]);
               dst4[1] = make_float4(t8[4], t8[5], t8[6], t8[7]);
             }
             epi_bar();
-            bias_sm = bias_s + buf * 128;
+            bias_sm = bias_s + buf * kAccStride;
           }
           mbar_wait(&acc_full[buf], par);
           tc_fence_after();
           if (tid == 0 && i == gw.p1 - 1) BD_STAMP(q, 3);
-          const uint32_t tbase = tmem_base + buf * 128u + (static_cast<uint32_t>(qd * 32) << 16);
+          const uint32_t tbase = tmem_base + buf * static_cast<uint32_t>(kAccStride) + (static_cast<uint32_t>(qd * 32) << 16);
           // 32-column chunks start at packed columns that are multiples of 32, so that every store is whole 32-byte
           // sectors; a pass that starts / ends mid-way gets a 16-column chunk at that edge
           int col = 0;

@@ -137,6 +137,9 @@ struct StreamProgram {
 // ---------------------------------------------------------------------------------------------------------------------
 // work partition of a GEMM op (shared by the packer, the three pipeline roles and the host)
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxPassUnits = 10;       // widest pass: 160 weight rows (TMEM: 3 accumulator buffers x 160 columns <= 512)
+constexpr int kAccStride = kMaxPassUnits * 16;
+
 struct StreamPart {
   int split;    // k-range index
   int unit0;    // first 16-row unit of this CTA
@@ -171,7 +174,10 @@ __host__ __device__ inline StreamPart stream_partition(int N, int K, int S, int 
   p.unit0 = static_cast<int>((static_cast<long long>(j) * U) / Gs);
   p.units = static_cast<int>((static_cast<long long>(j + 1) * U) / Gs) - p.unit0;
   p.kb0 = p.split * p.kbs;
-  p.npass = (p.units + 7) / 8;
+  // passes of <= 8 units (128 weight rows = one 16 KB ring half-slot per k-block) — except that a share of 9 or 10 units
+  // stays ONE pass of 144 / 160 rows: a second pass would re-read the whole activation operand for one or two units
+  // (measured on the k-split Linears wo / w2, 8.65 units per CTA: the MMA phase ran at 4.6 TB/s, bound by the A traffic)
+  p.npass = p.units <= kMaxPassUnits ? (p.units > 0 ? 1 : 0) : (p.units + 7) / 8;
   return p;
 }
 // pass i of a CTA covers units [pass_u0, pass_u1) relative to unit0
@@ -183,7 +189,9 @@ __host__ __device__ inline long long stream_pass_offset(int N, const StreamPart&
 }
 // the K loop advances in steps of kKbPerStep k-blocks (the last step may be short); rotation: CTAs start at different
 // steps so that they do not all hit the same L2 lines of A at once
-__host__ __device__ inline int stream_steps(int kbs) { return (kbs + kKbPerStep - 1) / kKbPerStep; }
+// k-blocks per ring step: 2 for passes of <= 128 rows (2 x 16 KB = one 32 KB slot), 1 for the wide single passes
+__host__ __device__ inline int stream_kps(int pass_rows) { return pass_rows <= 128 ? kKbPerStep : 1; }
+__host__ __device__ inline int stream_steps(int kbs, int kps = kKbPerStep) { return (kbs + kps - 1) / kps; }
 // mode (bd_stream_set_tuning, measurement): bit 3 = no rotation (every CTA walks K in the same order: the L2 sees ~148
 // requests for the same lines within a short window); bit 4 = CTAs rotate in groups of 4 (4 requesters per line)
 __host__ __device__ inline int stream_k_rot(int c, int nsteps, int mode = 0) {

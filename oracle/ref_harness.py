@@ -48,11 +48,11 @@ def import_reference():
     import types
 
     try:
-        if not torch.cuda.is_available():
-            raise ImportError("flash_attn has no CPU backend")
         import flash_attn  # noqa: F401
     except Exception:
+        import importlib.machinery
         m = types.ModuleType("flash_attn")
+        m.__spec__ = importlib.machinery.ModuleSpec("flash_attn", None)  # transformers probes find_spec("flash_attn")
         m.flash_attn_func = _eager_flash
         sys.modules["flash_attn"] = m
     mine = {k: v for k, v in sys.modules.items() if k == "modeling" or k.startswith("modeling.")}

@@ -1,0 +1,156 @@
+"""The oracle's autocast-bf16 mode (``rnd=bf16`` — what every GPU parity test compares against) pinned against the UNMODIFIED
+reference running on this GPU under the real ``torch.autocast("cuda", bfloat16)`` (the reference's deployment, t2i_pipeline.py:130),
+and the native engine against that same reference run end to end. Needs the verbatim copy of the reference that
+``oracle/make_ref.py`` ships under ``oracle/_ref`` (git-ignored); skipped when it is absent."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.reference]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_harness as rh
+    return rh.import_reference()
+
+
+def _ulps(a, b):
+    """max |a - b| in units of the bf16 spacing at max|b|"""
+    scale = b.abs().max().item()
+    return (a - b).abs().max().item() / (2.0 ** -8 * max(scale, 1e-6))
+
+
+def test_head_network_cuda_autocast_vs_oracle_bf16(ref):
+    from bitdance_b200.head import head_spec
+    from bitdance_b200.synth import synth_state_dict
+    from oracle import head as oh
+    cfg = dict(ch_target=32, ch_cond=256, ch_latent=256, depth_latent=4, depth_adanln=2, parallel_num=16, use_swiglu=True)
+    m = ref.fh.DiffHead(**cfg).eval()
+    sd = synth_state_dict(head_spec(32, 256, 256, 4, 2, True), seed=1, std=0.05)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    torch.manual_seed(0)
+    R, pn = 4, 16
+    x, t, c = torch.randn(R, pn, 32), torch.rand(R), torch.randn(R, pn, 256)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m.net(x.cuda(), t.cuda(), c.cuda()).float().cpu()
+    with torch.no_grad():
+        o_bf = oh.head_forward(sd, x, t, c, rnd=oh.bf16)
+        o_32 = oh.head_forward(sd, x, t, c, rnd=oh.ident)
+    e_bf, e_32 = (out - o_bf).abs().max().item(), (out - o_32).abs().max().item()
+    print(f"reference head under CUDA autocast vs oracle: rnd=bf16 max err {e_bf:.4f} ({_ulps(out, o_bf):.1f} bf16 ulps), "
+          f"rnd=ident (fp32) {e_32:.4f}")
+    assert _ulps(out, o_bf) <= 6.0          # same rounding points, different accumulation order (cuBLAS vs torch CPU)
+    assert e_bf <= e_32 + 1e-3              # the bf16 policy explains the reference's output at least as well as exact math
+
+
+def test_tokenizer_cuda_autocast_vs_oracle_bf16(ref):
+    from bitdance_b200.ae import ae_spec
+    from bitdance_b200.synth import synth_state_dict
+    from oracle import ae as oa
+    dd = dict(double_z=False, z_channels=32, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2], num_res_blocks=2)
+    m = ref.ae.VQModel(dd).eval()
+    sd = synth_state_dict(ae_spec(dd), seed=2, std=0.05)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 32, 48) * 2 - 1
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        lat = m.encoder(x.cuda()).float().cpu()
+        q = m.encode(x.cuda()).float().cpu()
+        dec = m.decode(q.cuda()).float().cpu()
+    with torch.no_grad():
+        q_o, lat_o = oa.encode(sd, x, rnd=oa.bf16)
+        dec_o = oa.decoder_forward(sd, q, rnd=oa.bf16)
+    e_lat = (lat - lat_o).abs().max().item()
+    print(f"reference tokenizer under CUDA autocast vs oracle rnd=bf16: latent err {e_lat:.4f} (scale {lat_o.abs().max().item():.2f}), "
+          f"token agreement {(q == q_o).float().mean().item():.4f}, decode err {(dec - dec_o).abs().max().item():.4f}")
+    assert e_lat < 2e-2 * lat_o.abs().max().item() + 1e-3
+    safe = lat_o.abs() > e_lat + 1e-3
+    assert torch.equal(q[safe], q_o[safe])
+    assert (dec - dec_o).abs().max().item() < 3e-2 * dec_o.abs().max().item() + 1e-2
+
+
+def test_llm_cuda_autocast_vs_oracle_bf16(ref):
+    """bf16 Qwen3 on the GPU exactly as the pipeline drives it: causal prefill (bf16 stream), first block with the all-ones
+    mask, then an AR block whose inputs_embeds are fp32 (bf16 MLP output + fp32 pos-embed, t2i_pipeline.py:253)."""
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    from bitdance_b200.llm import llm_spec
+    from bitdance_b200.synth import synth_state_dict
+    from oracle import llm as ol
+    c = dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+             head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6)
+    hf = Qwen3ForCausalLM(Qwen3Config(vocab_size=64, max_position_embeddings=512, tie_word_embeddings=False, **c)).eval()
+    spec = {k: tuple(v.shape) for k, v in hf.state_dict().items()}
+    sd = {k: v.to(torch.bfloat16).float() for k, v in synth_state_dict(spec, seed=3, std=0.05).items()}
+    hf.load_state_dict(sd)
+    hf = hf.to(torch.bfloat16).cuda()
+    torch.manual_seed(0)
+    B, pn = 2, 16
+    x0 = torch.randn(B, 9, 256).to(torch.bfloat16).float()
+    x1 = torch.randn(B, pn, 256).to(torch.bfloat16).float()
+    x2 = torch.randn(B, pn, 256)                                   # fp32 AR input
+    cache = [None] * 2
+    errs = []
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        o = hf.model(inputs_embeds=x0.to(torch.bfloat16).cuda(), use_cache=True)
+        pkv = o.past_key_values
+        r0 = ol.decoder_forward(sd, c, x0, cache, causal=True, rnd=ol.bf16, stream_f32=False)
+        errs.append(((o.last_hidden_state.float().cpu() - r0).abs().max() / r0.abs().max()).item())
+        for x, f32 in ((x1, False), (x2, True)):
+            mask = torch.ones(B, 1, pn, pn + pkv[0][0].shape[2], dtype=torch.bool, device="cuda")
+            xin = x.cuda() if f32 else x.to(torch.bfloat16).cuda()
+            o = hf.model(inputs_embeds=xin, past_key_values=pkv, use_cache=True, attention_mask=mask)
+            pkv = o.past_key_values
+            r = ol.decoder_forward(sd, c, x, cache, causal=False, rnd=ol.bf16, stream_f32=f32)
+            errs.append(((o.last_hidden_state.float().cpu() - r).abs().max() / r.abs().max()).item())
+    print("reference Qwen3 (transformers, bf16, CUDA autocast) vs oracle rnd=bf16, rel err prefill / block / fp32-stream AR block:",
+          [round(e, 4) for e in errs])
+    assert max(errs) < 3e-2
+
+
+def test_engine_vs_unmodified_reference_gen_image_on_gpu(ref):
+    """The whole ``gen_image`` of the reference on this GPU (tiny models, CUDA autocast, its own torch.randn draws recorded)
+    against the native engine fed the same token ids and the same noise: first-block tokens agree, decoded images are close."""
+    from oracle import ref_runner as rr
+    from bitdance_b200.synthetic import engine_from_state_dicts
+    pipe, info = rr.build_pipeline("tiny", "cuda")
+    m = rr.CONFIGS["tiny"]
+    pn = m["parallel_num"]
+    # export the reference's weights under the reference's own key names
+    hf = pipe.llm_model
+    sds = dict(llm={k: v.float().cpu() for k, v in hf.state_dict().items()},
+               head={k: v.float().cpu() for k, v in pipe.vision_head.state_dict().items()},
+               ae={k: v.float().cpu() for k, v in pipe.ae.state_dict().items()},
+               proj={k: v.float().cpu() for k, v in pipe.embed_vision_mlp.state_dict().items()})
+    S, guidance, B, px = 3, 3.0, 1, 32
+    rec = []
+    o1, o2 = torch.randn, torch.randn_like
+    torch.randn = lambda *a, **k: (rec.append(o1(*a, **k)) or rec[-1])
+    torch.randn_like = lambda a, **k: (rec.append(o2(a, **k)) or rec[-1])
+    try:
+        torch.manual_seed(11)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            img_ref = pipe.gen_image("cond", "uncond", guidance_scale=guidance, num_sampling_steps=S, max_length=64,
+                                     num_images=B, image_size=[px, px]).float().cpu()
+    finally:
+        torch.randn, torch.randn_like = o1, o2
+    steps = 64 // pn
+    assert len(rec) == steps * (S + 1)
+    noise = [torch.stack(rec[i * (S + 1):(i + 1) * (S + 1)]).float().contiguous() for i in range(steps)]
+    eng = engine_from_state_dicts(sds, "tiny", "cuda")
+    it = iter(noise)
+    eng.head.draw_noise = lambda b, p, s: next(it).cuda().contiguous()
+    tok = pipe.tokenizer
+    emb = sds["llm"]["model.embed_tokens.weight"]
+    bf = lambda ids: emb[ids].to(torch.bfloat16).cuda()
+    h = w = px // pipe.vae_patch_size
+    start = [tok.convert_tokens_to_ids("<|vision_start|>"), tok.convert_tokens_to_ids(f"<|res_{h}|>"),
+             tok.convert_tokens_to_ids(f"<|res_{w}|>")] + [tok.convert_tokens_to_ids(f"<|query_{i}|>") for i in range(1, pn)]
+    tokens, _ = eng.gen_tokens(bf(tok.encode("cond")), bf(tok.encode("uncond")), bf(start), h=h, w=w, num_images=B,
+                               guidance_scale=guidance, num_sampling_steps=S)
+    img = eng.decode(tokens, h, w).float().cpu()
+    d = (img - img_ref).abs()
+    print(f"engine vs the unmodified reference gen_image on this GPU: image |diff| max {d.max().item():.3f} mean "
+          f"{d.mean().item():.4f} (scale {img_ref.abs().max().item():.2f})")
+    assert d.mean().item() < 5e-2 * img_ref.abs().max().item()
