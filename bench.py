@@ -319,6 +319,12 @@ def main():
     roof = {} if args.no_roofline else dominant_kernel_roofline(eng, hbm_peak, peak_src, S, args.guidance, B)
     roof["ar_step"] = {"algorithmic_gb": step_bytes / 1e9, "ms": ms_ar, "achieved_gbs": step_bytes / 1e9 / (ms_ar / 1e3) if ms_ar else None,
                        "frac": (step_bytes / 1e9 / (ms_ar / 1e3)) / hbm_peak if ms_ar else None}
+    if R * pn > 128 and ms_ar:
+        step_flops = 2.0 * P_LLM * R * pn + (S + 1) * 2.0 * P_HEAD * R * pn
+        tpk = peaks.get("bf16_tflops_sustained", 1400.0)
+        roof["ar_step"].update({"bound": "tensor", "algorithmic_tflop": step_flops / 1e12,
+                                "achieved_tflops": step_flops / 1e12 / (ms_ar / 1e3),
+                                "frac_tensor": step_flops / 1e12 / (ms_ar / 1e3) / tpk})
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -397,6 +403,17 @@ def dominant_kernel_roofline(eng, hbm_peak, peak_src, S, guidance, B):
         return e0.elapsed_time(e1) / reps
 
     ms = timed(lambda: head.sample(z, guidance, S), 3)
+    if not stream_path:
+        # batch > one 128-row tile (bs >= 2 with CFG): M = R * pn rows per Linear is past the ridge (~280 rows at 2.25 PFLOP/s
+        # over 8 TB/s), the sampler is TENSOR-bound: algorithmic flops = (S + 1) evaluations x 2 x P_head x M rows
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+        flops = (S + 1) * 2.0 * P_HEAD * R * pn
+        ach = flops / 1e12 / (ms / 1e3)
+        return {"bound": "tensor", "kernel": "bd_head_sample multi-kernel path (bd_gemm_kernel, M = %d rows)" % (R * pn),
+                "achieved": ach, "peak": tpeak, "peak_source": "measured (sustained)" if peaks else "fallback", "unit": "TFLOP/s",
+                "frac": ach / tpeak, "traffic": None, "ms_per_launch": ms, "us_per_evaluation": ms * 1e3 / (S + 1),
+                "algorithmic_flops_per_launch": flops}
     bytes_alg = (S + 1) * 2 * (P_HEAD - P_COND) + 2 * P_COND
     ach = bytes_alg / 1e9 / (ms / 1e3)
     traffic = None
@@ -410,8 +427,9 @@ def dominant_kernel_roofline(eng, hbm_peak, peak_src, S, guidance, B):
            "kernel": ("bd_stream_kernel (persistent: one launch = DiffHead.sample, %d evaluations)" % (S + 1)) if stream_path
            else "bd_head_sample multi-kernel path (batch > one 128-row tile)",
            "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak,
-           "traffic": traffic, "ms_per_launch": ms, "us_per_evaluation": ms * 1e3 / (S + 1),
-           "algorithmic_bytes_per_launch": bytes_alg}
+           "traffic": traffic, "traffic_source": "profiles/r01_stream_kernel_ncu.json (ncu --set full of one launch of this "
+                                                 "kernel, committed; a citation, not a measurement of this run)",
+           "ms_per_launch": ms, "us_per_evaluation": ms * 1e3 / (S + 1), "algorithmic_bytes_per_launch": bytes_alg}
     if stream_path:
         N, K, nbuf = 3 * D, D, 4
         w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)

@@ -47,6 +47,11 @@ def import_reference():
         return _ns
     import types
 
+    # resolve transformers' lazy imports (qwen3 -> torchvision -> torch.library.register_fake -> inspect.getmodule) NOW:
+    # inspect.getmodule walks sys.modules and chokes on a namespace package without __file__, which is what the reference's
+    # top-level ``modeling`` is while it is being imported
+    from transformers import AutoTokenizer, Qwen3Config, Qwen3ForCausalLM, set_seed  # noqa: F401
+    from transformers.activations import ACT2FN  # noqa: F401
     try:
         import flash_attn  # noqa: F401
     except Exception:

@@ -14,6 +14,7 @@ for step in "$@"; do
     tests)    timeout 2400 python -m pytest tests -m gpu -q -s 2>&1 | grep -v "^    " > gpurun_out/${TAG}_tests.log ;;
     llmstream) BD_LLM_STREAM=1 timeout 900 python -m pytest tests/test_llm_gpu.py tests/test_pipeline_gpu.py -m gpu -q -s 2>&1 | grep -v "^    " | tail -80 > gpurun_out/${TAG}_test_llm_stream.log ;;
     benchllm) BD_LLM_STREAM=1 timeout 1500 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_llmstream.json 2> gpurun_out/${TAG}_bench_llmstream.err ;;
+    bench8)   timeout 1500 python bench.py --bs 8 --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_bs8.json 2> gpurun_out/${TAG}_bench_bs8.err ;;
     benchquick) timeout 1500 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_quick.json 2> gpurun_out/${TAG}_bench_quick.err ;;
     timeline) timeout 900 python scripts/head_timeline.py > gpurun_out/${TAG}_head_timeline.txt 2>&1 ;;
     ab)       timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab.txt 2>&1 ;;
