@@ -1,12 +1,30 @@
 #!/bin/bash
-# ncu evidence for the round (numbers printed by a run under ncu are never bench values):
-#  1. launch list: per-launch device time of every kernel of one truncated bench pass (prefill + 1 AR step);
-#  2. --set full capture of ONE launch of the dominant kernel, bd_stream_kernel (= one DiffHead.sample: 51 evaluations).
+# ncu evidence for the round (numbers printed by a run under ncu are never bench values). One truncated bench pass per
+# capture: prefill + 1 AR step (+ decode for the conv capture), CUDA graph off so that every kernel is visible.
+#   1. launch list: per-launch device time of every kernel (shares of the step);
+#   2. --set full of the persistent kernel: first launch = one DiffHead.sample (51 evaluations), second = one Qwen3 AR block;
+#   3. --set full of the tiled GEMM (prefill), the attention kernel (prefill) and the tokenizer convolution (decode).
+set +e
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-BENCH="python bench.py --steps 1 --warmup 0 --ar-steps 1 --graph 0 --no-cpu-baseline --no-roofline"
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NLAUNCH:-6000} --csv \
-    --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_list.log 2>&1
-echo "launch list rc=$? lines=$(wc -l < gpurun_out/launches.csv)"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:bd_stream_kernel -s ${KSKIP:-1} -c 1 -f \
-    -o gpurun_out/prof_stream $BENCH > gpurun_out/ncu_full.log 2>&1
-echo "full capture rc=$?"; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/*.ncu-rep 2>/dev/null
+TAG=${TAG:-r02}
+export BD_LLM_STREAM=${BD_LLM_STREAM:-1}
+BENCH="python bench.py --steps 1 --warmup 0 --ar-steps 1 --graph 0 --no-cpu-baseline --no-gpu-reference --no-roofline"
+FULL="python bench.py --steps 1 --warmup 0 --ar-steps 64 --graph 1 --no-cpu-baseline --no-gpu-reference --no-roofline"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NLAUNCH:-4000} --csv \
+    --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_ncu_list.log 2>&1
+echo "launch list rc=$? lines=$(wc -l < gpurun_out/${TAG}_launches.csv)"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:bd_stream_kernel -c 2 -f \
+    -o gpurun_out/${TAG}_prof_stream $BENCH > gpurun_out/${TAG}_ncu_stream.log 2>&1
+echo "stream capture rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_gemm_kernel -s 4 -c 3 -f \
+    -o gpurun_out/${TAG}_prof_gemm $BENCH > gpurun_out/${TAG}_ncu_gemm.log 2>&1
+echo "gemm capture rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_attn_kernel -s 2 -c 2 -f \
+    -o gpurun_out/${TAG}_prof_attn $BENCH > gpurun_out/${TAG}_ncu_attn.log 2>&1
+echo "attn capture rc=$?"
+# the conv capture needs the decode: a small script instead of a whole image (encode + decode of one 1024^2 image)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_conv_kernel -s 20 -c 3 -f \
+    -o gpurun_out/${TAG}_prof_conv python scripts/ae_bench.py --bs 1 --reps 1 > gpurun_out/${TAG}_ncu_conv.log 2>&1
+echo "conv capture rc=$?"
+ls -la gpurun_out/${TAG}_prof_*.ncu-rep 2>/dev/null
