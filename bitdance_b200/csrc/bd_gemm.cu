@@ -1,4 +1,5 @@
 // bd_gemm.cu — C-ABI for the weight-streaming tcgen05 GEMM (kernel in bd_gemm.cuh).
+#include <cstdlib>
 #include "bd_gemm.cuh"
 #include "bd_host.h"
 
@@ -48,6 +49,45 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, int M, int 
   // Re-reading A across N tiles should hit L2: ask TMA to keep it when it is small next to W.
   const int a_hint_last = (static_cast<long long>(M) * K * 2 <= (32ll << 20)) ? 1 : 0;
   BD_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, bd_gemm_kernel<BN>, ta, tw, M, N, K, splits, partial, epi, a_hint_last, w_tiled));
+  return BD_OK;
+}
+
+// CTA-pair kernel (bd_gemm2_kernel): clusters of 2 along M. BD_GEMM2=0 switches it off (A/B measurements).
+static int gemm2_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BD_GEMM2");
+    v = (e && *e) ? atoi(e) : 1;
+  }
+  return v;
+}
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, const GemmEpi& epi, bool pdl,
+                        cudaStream_t stream) {
+  {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    BD_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      BD_CUDA_TRY(cudaFuncSetAttribute(bd_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * ((M + 255) / 256), (N + 255) / 256, 1);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = Gemm2Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  ++g_launch_count;
+  BD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bd_gemm2_kernel, ta, tw, M, N, K, epi));
   return BD_OK;
 }
 
@@ -104,6 +144,17 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   BD_REQUIRE(lda >= K && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0);
   BD_REQUIRE(!epi.swiglu || ((N % 32) == 0 && !epi.gate && !epi.res && !epi.out_f32 && epi.act == 0));
   GemmPlan p = plan_gemm(M, N, K, bn, splits);
+  // compute-bound shapes: the CTA-pair kernel (256 x 256 tiles, cta_group::2) on tile-major weights
+  if (w_tiled && M >= 256 && (N % 256) == 0 && bn == 0 && splits == 0 && !partial_splits && gemm2_enabled()) {
+    CUtensorMap ta2, tw2;
+    int rc2 = make_tmap_2d_bf16(&ta2, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda),
+                                kGemmBK, kGemmBM);
+    if (rc2 != BD_OK) return rc2;
+    const uint64_t rows2 = static_cast<uint64_t>((N + 127) / 128) * ((K + 63) / 64) * 128;
+    rc2 = make_tmap_2d_bf16(&tw2, W, 64, rows2, 64, kGemmBK, 128);
+    if (rc2 != BD_OK) return rc2;
+    return launch_gemm2(ta2, tw2, M, N, K, epi, pdl, stream);
+  }
   float* partial = nullptr;
   if (p.splits > 1) {
     const size_t need = static_cast<size_t>(p.splits) * M * N * sizeof(float);

@@ -361,6 +361,118 @@ bd_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant for COMPUTE-bound shapes (M >= 256 rows: batches of images, prefill, the ImageNet generator): a cluster
+// of two CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of A and HALF of
+// the 256 weight rows, so a k-block costs 32 KB of shared-memory ingest per SM instead of 48 KB (the 1-CTA 128 x 256 tile is
+// ingest-bound at ~60 % of the tensor peak). Tile-major W only, no split-K; the epilogue is the 1-CTA one on the CTA's own
+// 128 accumulator rows.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;       // 16 KB: this CTA's 128 rows
+  static constexpr int kWBytes = (BN / 2) * kGemmBK * 2;      // 16 KB: this CTA's half of the weight rows
+  static constexpr int kStageBytes = kABytes + kWBytes;
+  static constexpr int kStages = 6;
+  static constexpr int kBarBytes = (2 * kStages + 1) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
+  static constexpr uint32_t kTmemCols = 256;
+};
+
+static __global__ void __launch_bounds__(kConvThreads, 1)
+bd_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M, int N,
+                int K, GemmEpi epi) {
+  using Cfg = Gemm2Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_bar = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = (blockIdx.x >> 1) * 256 + static_cast<int>(rank) * kGemmBM;
+  const int n0 = blockIdx.y * Cfg::BN;
+  const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_a);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  grid_dep_launch();
+
+  if (warp == 0) {
+    // ===== producer (each CTA): its A rows and its half of the W rows; bytes are counted on the LEADER's full barrier =====
+    if (elect_one()) {
+      grid_dep_wait();
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % Cfg::kStages;
+        if (i >= Cfg::kStages) mbar_wait(&empty[s], (static_cast<uint32_t>(i / Cfg::kStages) & 1u) ^ 1u);
+        if (rank == 0) mbar_expect_tx(&full[s], 2u * Cfg::kStageBytes);
+        uint8_t* dst = smem + s * Cfg::kStageBytes;
+        tma_load_2d_2sm(dst, &tmap_a, &full[s], i * kGemmBK, m0, kEvictNormal);
+        // tile-major W [n_tile(128 rows)][k_block][128][64]: this CTA's half = n_tile (n0 / 128 + rank)
+        tma_load_2d_2sm(dst + Cfg::kABytes, &tmap_w, &full[s], 0, ((n0 / 128 + static_cast<int>(rank)) * num_kb + i) * 128,
+                        kEvictNormal);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA only =====
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, Cfg::BN);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % Cfg::kStages;
+        mbar_wait(&full[s], static_cast<uint32_t>(i / Cfg::kStages) & 1u);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t w_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < kGemmBK / 16; ++k)
+          umma_bf16_2sm(tmem_base, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(w_addr + k * 32), idesc,
+                        (i | k) != 0 ? 1u : 0u);
+        umma_commit_2sm(&empty[s]);  // frees the stage in BOTH CTAs once these MMAs retire
+      }
+      umma_commit_2sm(acc_bar);
+    }
+  } else {
+    // ===== epilogue: warps 2..5 of each CTA on its own 128 accumulator rows =====
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + static_cast<int>(lane_id());
+    grid_dep_wait();
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < Cfg::BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+      tmem_ld_wait();
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+      const int nc = n0 + c * 32;
+      if (m < M && nc < N) epi_apply_store(epi, acc, m, nc, N);
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();  // the peer may still read this CTA's shared memory / signal its barriers until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
 // Deterministic split-K reduction + epilogue: one thread per (row, 32-column chunk).
 static __global__ void __launch_bounds__(256) bd_splitk_epilogue_kernel(const float* __restrict__ partial, int M, int N,
                                                                   int splits, GemmEpi epi) {

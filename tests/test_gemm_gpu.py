@@ -127,3 +127,36 @@ def test_gemm_deterministic():
     o2 = ops.gemm(a, w)
     torch.cuda.synchronize()
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (256, 256, 64),          # one cluster, one k-block
+    (1024, 5120, 5120),      # bs=8 head / LLM Linear
+    (1000, 768, 768 + 32),   # ragged M (TMA zero fill in the second CTA of the last pair), ragged K
+    (384, 15360, 512),       # M = 1.5 pairs: the odd CTA of the last pair has no valid rows
+    (4096, 2304, 768),       # ImageNet-B qkv at batch 256 x 16 tokens
+])
+def test_gemm_cta_pair_kernel(M, N, K):
+    """bd_gemm2_kernel (tcgen05.mma.cta_group::2, clusters of two CTAs on 256 x 256 tiles; chosen automatically for
+    tile-major weights, M >= 256, N % 256 == 0) against torch and — bit for bit — against the 1-CTA kernel (same K order,
+    same fp32 accumulation), with the bias / residual / SwiGLU epilogues."""
+    from bitdance_b200 import ops
+    torch.manual_seed(0)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    bias = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16)
+    res = torch.randn(M, N, device="cuda")
+    pw = ops.pack_weight(w)
+    out2 = ops.gemm(a, pw, bias=bias)                     # auto plan -> CTA-pair kernel
+    out1 = ops.gemm(a, pw, bias=bias, bn=256, splits=1)   # explicit tile: the 1-CTA kernel
+    check_close(out2, ref_linear(a, w, bias), K, "pair")
+    assert torch.equal(out2, out1), "CTA-pair and 1-CTA kernels differ"
+    o32 = ops.gemm(a, pw, bias=bias, res=res, out_dtype=torch.float32)
+    check_close(o32, ref_linear(a, w, bias, res=res, out_dtype=torch.float32), K, "pair+res")
+    if N % 32 == 0:
+        wi, bi = ops.interleave16(w[:N // 2].contiguous(), w[N // 2:].contiguous(), bias[:N // 2].contiguous(),
+                                  bias[N // 2:].contiguous())
+        osw = ops.gemm(a, ops.pack_weight(wi), bias=bi, swiglu=True)
+        y = bf(a.float() @ w.float().t() + bias.float())
+        ref = bf(bf(torch.nn.functional.silu(y[:, :N // 2])) * y[:, N // 2:])
+        check_close(osw, ref, K, "pair+swiglu")
