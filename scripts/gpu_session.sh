@@ -16,6 +16,9 @@ for step in "$@"; do
     benchllm) BD_LLM_STREAM=1 timeout 1500 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_llmstream.json 2> gpurun_out/${TAG}_bench_llmstream.err ;;
     bench8)   timeout 1500 python bench.py --bs 8 --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_bs8.json 2> gpurun_out/${TAG}_bench_bs8.err ;;
     benchquick) timeout 1500 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_quick.json 2> gpurun_out/${TAG}_bench_quick.err ;;
+    gemmtest) timeout 900 python -m pytest tests/test_gemm_gpu.py -m gpu -q -s 2>&1 | grep -v "^    " | tail -40 > gpurun_out/${TAG}_test_gemm.log ;;
+    llmtl)    timeout 900 python scripts/llm_timeline.py > gpurun_out/${TAG}_llm_timeline.txt 2>&1 ;;
+    bench8g0) BD_GEMM2=0 timeout 1500 python bench.py --bs 8 --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-reference > gpurun_out/${TAG}_bench_bs8_gemm1cta.json 2> gpurun_out/${TAG}_bench_bs8_gemm1cta.err ;;
     timeline) timeout 900 python scripts/head_timeline.py > gpurun_out/${TAG}_head_timeline.txt 2>&1 ;;
     ab)       timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab.txt 2>&1 ;;
     ab_r01)   BD_LIB_PATH=$PWD/ab/libbitdance_b200_r01.so timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab_r01.txt 2>&1 ;;
