@@ -362,14 +362,17 @@ static int llm_stream_all(const bd_llm_weights_t& w, void* hidden, int R, int S,
   prog.sync = reinterpret_cast<unsigned int*>(base + L.s_sync);
   const void* const* tab = static_cast<const void* const*>(w.layer_tab);
   enum { T_WQKV = 1, T_WO, T_WGU, T_WDOWN, T_LN1, T_LN2, T_QN, T_KN };  // slot + 1
-  // split of the key range: balance (units per CTA) x (key tiles per unit)
-  const int n_tiles = (sk_bound + 63) / 64;
+  // split of the key range: balance (units per CTA) x (key tiles per unit + a per-unit cost of ~2 tiles: Q / first K, V
+  // fetch, partial store) at ~60 % of the planning bound — the cache grows from the prompt to sk_bound over an image and
+  // the split count is fixed for a captured graph; fewer splits also mean less partial traffic for the combine
+  const int n_tiles_max = (sk_bound + 63) / 64;
+  const int n_tiles = n_tiles_max > 4 ? (n_tiles_max * 3 + 4) / 5 : n_tiles_max;
   int splits = 1;
   {
     double best = 1e30;
     for (int s = 1; s <= kLlmMaxSplits && s <= n_tiles; ++s) {
       const int rounds = (R * w.Hq * s + G - 1) / G;
-      const double cost = rounds * ((n_tiles + s - 1) / s + 1.0);
+      const double cost = rounds * ((n_tiles + s - 1) / s + 2.0) + 0.25 * s;
       if (cost < best) {
         best = cost;
         splits = s;

@@ -648,19 +648,44 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       for (int v = tid; v < Hq * vph; v += 128) {
         const int h = v / vph, d0 = (v % vph) * 8;
         const long long row = (static_cast<long long>(b) * Hq + h) * S + sq;
+        constexpr int kMaxS = 16;
+        float ms[kMaxS], ls[kMaxS];
+#pragma unroll
+        for (int sp = 0; sp < kMaxS; ++sp) {
+          ms[sp] = -FLT_MAX;
+          ls[sp] = 0.f;
+          if (sp < splits) {
+            const float2 t = __ldcg(reinterpret_cast<const float2*>(part_ml + (sp * rows + row) * 2));
+            ms[sp] = t.x;
+            ls[sp] = t.y;
+          }
+        }
         float mx = -FLT_MAX;
-        for (int sp = 0; sp < splits; ++sp) mx = fmaxf(mx, __ldcg(part_ml + (sp * rows + row) * 2));
+#pragma unroll
+        for (int sp = 0; sp < kMaxS; ++sp) mx = fmaxf(mx, ms[sp]);
         float l = 0.f, acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int sp = 0; sp < splits; ++sp) {
-          const float ms = __ldcg(part_ml + (sp * rows + row) * 2), ls = __ldcg(part_ml + (sp * rows + row) * 2 + 1);
-          const float wgt = (ls > 0.f) ? exp2f(ms - mx) : 0.f;
-          l += ls * wgt;
-          const float* o = part_o + (sp * rows + row) * HD + d0;
-          const float4 x0 = ldcg_f4(o), x1 = ldcg_f4(o + 4);
-          acc[0] += x0.x * wgt; acc[1] += x0.y * wgt; acc[2] += x0.z * wgt; acc[3] += x0.w * wgt;
-          acc[4] += x1.x * wgt; acc[5] += x1.y * wgt; acc[6] += x1.z * wgt; acc[7] += x1.w * wgt;
+#pragma unroll
+        for (int s0 = 0; s0 < kMaxS; s0 += 4) {
+          if (s0 >= splits) break;
+          float4 x0[4], x1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            x0[u] = x1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s0 + u < splits) {
+              const float* o = part_o + ((s0 + u) * rows + row) * HD + d0;
+              x0[u] = ldcg_f4(o);
+              x1[u] = ldcg_f4(o + 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {  // split order: deterministic
+            const float wgt = (ls[s0 + u] > 0.f) ? exp2f(ms[s0 + u] - mx) : 0.f;
+            l += ls[s0 + u] * wgt;
+            acc[0] += x0[u].x * wgt; acc[1] += x0[u].y * wgt; acc[2] += x0[u].z * wgt; acc[3] += x0[u].w * wgt;
+            acc[4] += x1[u].x * wgt; acc[5] += x1[u].y * wgt; acc[6] += x1[u].z * wgt; acc[7] += x1[u].w * wgt;
+          }
         }
         const float inv = l > 0.f ? 1.0f / l : 0.f;
         float y[8];
@@ -871,67 +896,93 @@ __device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int 
   __nv_bfloat16* kpool = reinterpret_cast<__nv_bfloat16*>(op.o1) + static_cast<long long>(it) * op.l0;
   __nv_bfloat16* vpool = kpool + op.l1;
   const long long tasks = static_cast<long long>(M) * heads;
-  for (long long gw = static_cast<long long>(c) * 4 + warp; gw < tasks; gw += static_cast<long long>(G) * 4) {
-    const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
-    const int b = m / S, s = m % S;
-    const int pos = __ldcg(seq_lens + b) + s;
-    if (pos < 0 || pos >= max_pages * 64) {
-      if (lane == 0) printf("bd_stream: sequence %d position %d outside the KV cache (%d tokens)\n", b, pos, max_pages * 64);
-      __trap();
-    }
-    const __nv_bfloat16* src = qkv + static_cast<long long>(m) * heads * HD + static_cast<long long>(hh) * HD + lane * VPT;
-    float x[VPT];
-    if constexpr (VPT == 4) {
-      const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(src));
-      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-      const float2 a = __bfloat1622float2(p2[0]), bb = __bfloat1622float2(p2[1]);
-      x[0] = a.x; x[1] = a.y; x[2] = bb.x; x[3] = bb.y;
-    } else {
-      const uint32_t raw = __ldcg(reinterpret_cast<const uint32_t*>(src));
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
-      x[0] = a.x; x[1] = a.y;
-    }
-    const bool is_q = hh < Hq, is_k = !is_q && hh < Hq + Hkv;
-    __nv_bfloat16* dst;
-    if (is_q) {
-      dst = q_out + static_cast<long long>(m) * Hq * HD + static_cast<long long>(hh) * HD;
-    } else {
-      const int hk = is_k ? hh - Hq : hh - Hq - Hkv;
-      const int page = page_table[b * max_pages + pos / 64];
-      dst = (is_k ? kpool : vpool) + ((static_cast<long long>(page) * Hkv + hk) * 64 + (pos % 64)) * HD;
-    }
-    float y[VPT];
-    if (!is_q && !is_k) {  // V: plain copy
+  const long long stride = static_cast<long long>(G) * 4;
+  constexpr int U = 4;  // tasks in flight per warp: a task is a chain of ~4 dependent L2 round trips, 12 tasks per warp
+  for (long long gw0 = static_cast<long long>(c) * 4 + warp; gw0 < tasks; gw0 += stride * U) {
+    float x[U][VPT], cs[U][VPT], sn[U][VPT];
+    int pos[U], page[U];
+    bool live[U];
 #pragma unroll
-      for (int j = 0; j < VPT; ++j) y[j] = x[j];
-    } else {
-      float ss = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long gw = gw0 + u * stride;
+      live[u] = gw < tasks;
+      pos[u] = 0;
+      page[u] = 0;
 #pragma unroll
-      for (int j = 0; j < VPT; ++j) ss += x[j] * x[j];
+      for (int j = 0; j < VPT; ++j) x[u][j] = cs[u][j] = sn[u][j] = 0.f;
+      if (!live[u]) continue;
+      const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
+      const int b = m / S, sidx = m % S;
+      pos[u] = __ldcg(seq_lens + b) + sidx;
+      if (pos[u] < 0 || pos[u] >= max_pages * 64) {
+        if (lane == 0) printf("bd_stream: sequence %d position %d outside the KV cache (%d tokens)\n", b, pos[u], max_pages * 64);
+        __trap();
+      }
+      const __nv_bfloat16* src = qkv + static_cast<long long>(m) * heads * HD + static_cast<long long>(hh) * HD + lane * VPT;
+      if constexpr (VPT == 4) {
+        const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(src));
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const float2 a = __bfloat1622float2(p2[0]), bb = __bfloat1622float2(p2[1]);
+        x[u][0] = a.x; x[u][1] = a.y; x[u][2] = bb.x; x[u][3] = bb.y;
+      } else {
+        const uint32_t raw = __ldcg(reinterpret_cast<const uint32_t*>(src));
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
+        x[u][0] = a.x; x[u][1] = a.y;
+      }
+      if (hh >= Hq) page[u] = __ldg(page_table + b * max_pages + pos[u] / 64);
+      if (hh < Hq + Hkv) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float rstd = rsqrtf(ss / static_cast<float>(HD) + op.f0);
-      const __nv_bfloat16* nw = is_q ? qn_w : kn_w;
-#pragma unroll
-      for (int j = 0; j < VPT; ++j) x[j] = bf16_round(__bfloat162float(nw[lane * VPT + j]) * bf16_round(x[j] * rstd));
-#pragma unroll
-      for (int j = 0; j < VPT; ++j) {
-        const float other = __shfl_xor_sync(0xffffffffu, x[j], 16);
-        const float rot = (lane < 16) ? -other : other;  // rotate_half: cat(-x2, x1)
-        const int d = lane * VPT + j;
-        const float cs = rope_cos[static_cast<long long>(pos) * HD + d], sn = rope_sin[static_cast<long long>(pos) * HD + d];
-        y[j] = __fadd_rn(__fmul_rn(x[j], cs), __fmul_rn(rot, sn));
+        for (int j = 0; j < VPT; ++j) {
+          cs[u][j] = __ldg(rope_cos + static_cast<long long>(pos[u]) * HD + lane * VPT + j);
+          sn[u][j] = __ldg(rope_sin + static_cast<long long>(pos[u]) * HD + lane * VPT + j);
+        }
       }
     }
-    if constexpr (VPT == 4) {
-      uint2 pk;
-      __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]), bb = __floats2bfloat162_rn(y[2], y[3]);
-      pk.x = *reinterpret_cast<uint32_t*>(&a);
-      pk.y = *reinterpret_cast<uint32_t*>(&bb);
-      *reinterpret_cast<uint2*>(dst + lane * VPT) = pk;
-    } else {
-      __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]);
-      *reinterpret_cast<uint32_t*>(dst + lane * VPT) = *reinterpret_cast<uint32_t*>(&a);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;   // warp-uniform
+      const long long gw = gw0 + u * stride;
+      const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
+      const bool is_q = hh < Hq, is_k = !is_q && hh < Hq + Hkv;
+      __nv_bfloat16* dst;
+      if (is_q) {
+        dst = q_out + static_cast<long long>(m) * Hq * HD + static_cast<long long>(hh) * HD;
+      } else {
+        const int hk = is_k ? hh - Hq : hh - Hq - Hkv;
+        dst = (is_k ? kpool : vpool) + ((static_cast<long long>(page[u]) * Hkv + hk) * 64 + (pos[u] % 64)) * HD;
+      }
+      float y[VPT];
+      if (!is_q && !is_k) {  // V: plain copy
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) y[j] = x[u][j];
+      } else {
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) ss += x[u][j] * x[u][j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float rstd = rsqrtf(ss / static_cast<float>(HD) + op.f0);
+        const __nv_bfloat16* nw = is_q ? qn_w : kn_w;
+        float xn[VPT];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) xn[j] = bf16_round(__bfloat162float(nw[lane * VPT + j]) * bf16_round(x[u][j] * rstd));
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const float other = __shfl_xor_sync(0xffffffffu, xn[j], 16);
+          const float rot = (lane < 16) ? -other : other;  // rotate_half: cat(-x2, x1)
+          y[j] = __fadd_rn(__fmul_rn(xn[j], cs[u][j]), __fmul_rn(rot, sn[u][j]));
+        }
+      }
+      if constexpr (VPT == 4) {
+        uint2 pk;
+        __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]), bb = __floats2bfloat162_rn(y[2], y[3]);
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&bb);
+        *reinterpret_cast<uint2*>(dst + lane * VPT) = pk;
+      } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]);
+        *reinterpret_cast<uint32_t*>(dst + lane * VPT) = *reinterpret_cast<uint32_t*>(&a);
+      }
     }
   }
 }
