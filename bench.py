@@ -26,6 +26,7 @@ MODEL = "BitDance-14B-64x"
 METRIC = "1024px images/sec (14B-64x)"
 P_LLM, P_HEAD, P_COND, P_PROJ = 13.2125e9, 1.7585e9, 26.2e6, 26.4e6
 KV_BYTES_PER_TOKEN = 163840
+DEFAULT_LLM_STREAM = False   # set from the round's A/B (profiles/): one persistent launch per Qwen3 AR block
 
 
 def algorithmic_bytes_per_ar_step(R: int, S: int, avg_ctx: float) -> float:
@@ -166,6 +167,8 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the GPU-eager reference leg")
     ap.add_argument("--no-roofline", action="store_true", help="profiling runs: skip the live dominant-kernel timing")
     ap.add_argument("--graph", type=int, default=1, help="replay the AR step as a CUDA graph (1) or launch it eagerly (0)")
+    ap.add_argument("--llm-stream", type=int, default=-1,
+                    help="Qwen3 AR block as one persistent launch (1) or as chained kernels (0); -1: BD_LLM_STREAM or the default")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -191,7 +194,10 @@ def main():
     lib = _lib.load()
     lib.bd_launch_count.restype = __import__("ctypes").c_ulonglong
     _lib.check(lib.bd_device_check(), "bd_device_check")
-    eng, embed = build_synthetic_engine(args.model, dev, seed=rank)
+    llm_stream = None if args.llm_stream < 0 else bool(args.llm_stream)
+    if llm_stream is None and "BD_LLM_STREAM" not in os.environ:
+        llm_stream = DEFAULT_LLM_STREAM
+    eng, embed = build_synthetic_engine(args.model, dev, seed=rank, llm_stream=llm_stream)
     eng.use_graph = bool(args.graph)
     collectives = {}
     if world > 1:
@@ -333,7 +339,8 @@ def main():
                                f"CFG {args.guidance}, S={S} (+1), synthetic 64-token prompt",
                    "parallelism": f"replicas x{world} (independent images per GPU, no data-path collective)",
                    "l2": "inputs >> L2: 33 GB of bf16 weights streamed per AR step",
-                   "cuda_graph": bool(args.graph), "ms_per_ar_step": ms_ar, "prefill_ms": 1e3 * phases.get("prefill_s", 0.0),
+                   "cuda_graph": bool(args.graph), "llm_ar_block": "one persistent launch" if eng.llm.w.layer_tab else "chained kernels",
+                   "ms_per_ar_step": ms_ar, "prefill_ms": 1e3 * phases.get("prefill_s", 0.0),
                    "truncated_ar_steps": args.ar_steps},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(e2e_h2d),

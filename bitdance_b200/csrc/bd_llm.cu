@@ -262,6 +262,7 @@ static int llm_stream_segment(const bd_llm_weights_t& w, int li, bool first, voi
                               int out_add_mod, cudaStream_t st) {
   static thread_local StreamProgram prog;
   prog = StreamProgram{};
+  prog.family = kStreamFamLlm;
   prog.M = M;
   prog.n_ctas = w.stream_ctas;
   prog.n_iter = 1;
@@ -355,6 +356,7 @@ static int llm_stream_all(const bd_llm_weights_t& w, void* hidden, int R, int S,
   BD_REQUIRE(w.n_layers <= kStreamMaxIter && S <= 64 && R * w.Hq <= 4096);
   static thread_local StreamProgram prog;
   prog = StreamProgram{};
+  prog.family = kStreamFamLlm;
   prog.M = M;
   prog.n_ctas = G;
   prog.n_iter = w.n_layers;
@@ -362,23 +364,13 @@ static int llm_stream_all(const bd_llm_weights_t& w, void* hidden, int R, int S,
   prog.sync = reinterpret_cast<unsigned int*>(base + L.s_sync);
   const void* const* tab = static_cast<const void* const*>(w.layer_tab);
   enum { T_WQKV = 1, T_WO, T_WGU, T_WDOWN, T_LN1, T_LN2, T_QN, T_KN };  // slot + 1
-  // split of the key range: balance (units per CTA) x (key tiles per unit + a per-unit cost of ~2 tiles: Q / first K, V
-  // fetch, partial store) at ~60 % of the planning bound — the cache grows from the prompt to sk_bound over an image and
-  // the split count is fixed for a captured graph; fewer splits also mean less partial traffic for the combine
-  const int n_tiles_max = (sk_bound + 63) / 64;
-  const int n_tiles = n_tiles_max > 4 ? (n_tiles_max * 3 + 4) / 5 : n_tiles_max;
-  int splits = 1;
-  {
-    double best = 1e30;
-    for (int s = 1; s <= kLlmMaxSplits && s <= n_tiles; ++s) {
-      const int rounds = (R * w.Hq * s + G - 1) / G;
-      const double cost = rounds * ((n_tiles + s - 1) / s + 2.0) + 0.25 * s;
-      if (cost < best) {
-        best = cost;
-        splits = s;
-      }
-    }
-  }
+  // attention: the (sequence, q head, 32-key half tile) items are dealt evenly over the first att_ctas CTAs whatever the
+  // lengths are (bd_stream.cu: llm_attn_stream); a (sequence, head) block is touched by at most att_ctas / Hq + 2 CTAs,
+  // one partial slot each (+1 slack; the kernel traps beyond). The bound on att_ctas keeps the slots within the
+  // kLlmMaxSplits the workspace is sized for.
+  const int att_ctas = std::min(G, (kLlmMaxSplits - 3) * w.Hq);
+  const int splits = att_ctas / w.Hq + 3;
+  (void)sk_bound;
   float* part_o = reinterpret_cast<float*>(base + L.attn);
   float* part_ml = part_o + static_cast<size_t>(splits) * R * w.Hq * S * hd;
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(base + L.qkv);
@@ -459,6 +451,7 @@ static int llm_stream_all(const bd_llm_weights_t& w, void* hidden, int R, int S,
     op.o1 = part_ml;
     op.sub = R;
     op.ksplit = splits;
+    op.act = att_ctas;
     op.i0 = S;
     op.i1 = w.Hq;
     op.i2 = w.Hkv;
@@ -471,6 +464,8 @@ static int llm_stream_all(const bd_llm_weights_t& w, void* hidden, int R, int S,
     op.sub = kRowLlmAttnCombine;
     op.p0 = part_o;
     op.p1 = part_ml;
+    op.p2 = seq_lens;
+    op.act = att_ctas;
     op.i0 = splits;
     op.i1 = w.Hq;
     op.i2 = S;

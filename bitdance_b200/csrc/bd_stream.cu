@@ -106,6 +106,11 @@ __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m,
 
 // ---------------------------------------------------------------------------------------------------------------------
 // row ops: executed by the 128 epilogue threads of CTA r for token row r
+// split-KV attention of an AR block (llm_attn_stream below): the CTA whose range [c P / Ge, (c + 1) P / Ge) holds item f
+__device__ __forceinline__ int llm_attn_cta_of(long long f, int Ge, int P) {
+  return static_cast<int>(((f + 1) * Ge - 1) / P);  // the CTA whose range [c P / Ge, (c + 1) P / Ge) holds f
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // A row op is a chain of L2 round trips, not a bandwidth problem (there is no L1 left beside 226 KB of shared memory): the
 // round-1 version issued its loads iteration by iteration — every 16-byte store to the row (which may alias in the
@@ -477,9 +482,14 @@ __device__ __forceinline__ void llm_res_rms(const StreamOp& op, int M, int r, in
   }
 }
 
+// FAM: the kernel is compiled once per program family (kStreamFamHead: the diffusion head's row ops + per-(sequence,
+// head) attention; kStreamFamLlm: the Qwen3 block's) — each instance carries only its own executors, so that neither
+// pays for the other's registers and instruction footprint.
+template <int FAM>
 __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp& op, int it, int r, int tid, float* red,
                                        uint8_t* scratch) {
   const int M = prog.M;
+  if constexpr (FAM == kStreamFamHead) {
   switch (op.sub) {
     case kRowCastCond: {  // p0 fp32 [M, N] (kernel input) -> o0 blocked bf16
       if (r >= M) return;
@@ -633,29 +643,44 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       }
       return;
     }
+    default: return;
+  }
+  } else {
+  switch (op.sub) {
     case kRowLlmAttnCombine: {
-      // token row r = (sequence b, position s): reduce the split-KV partials of every q head in split order (the arithmetic of
-      // bd_attn.cu::bd_attn_combine_kernel) -> bf16 -> blocked operand of o_proj. p0 partial O fp32 [splits][R][Hq][S][hd],
-      // p1 partial (max, sum) [splits][R][Hq][S][2], i0 = splits, i1 = Hq, i2 = S, K = hd, o0 = out blocked
+      // token row r = (sequence b, position s): reduce the segments of every (b, q head) block in slot order (see
+      // llm_attn_stream: same geometry) -> bf16 -> blocked operand of o_proj. p0 partial O fp32 [R Hq][i0][S][hd], p1
+      // partial (max, sum) [R Hq][i0][S][2], p2 seq_lens, i0 = slots per block, i1 = Hq, i2 = S, act = CTA bound of the
+      // attention op, K = hd, o0 = out blocked
       if (r >= M) return;
-      const int HD = op.K, Hq = op.i1, S = op.i2, splits = op.i0, R = M / S;
+      const int HD = op.K, Hq = op.i1, S = op.i2, maxseg = op.i0, R = M / S;
       const int b = r / S, sq = r % S;
       const float* part_o = reinterpret_cast<const float*>(op.p0);
       const float* part_ml = reinterpret_cast<const float*>(op.p1);
-      const long long rows = static_cast<long long>(R) * Hq * S;
+      const int* seq_lens = reinterpret_cast<const int*>(op.p2);
+      int P = 0, base = 0, T32 = 0;
+      for (int bb = 0; bb < R; ++bb) {
+        const int tb = (__ldcg(seq_lens + bb) + S + 31) >> 5;
+        if (bb < b) base += Hq * tb;
+        if (bb == b) T32 = tb;
+        P += Hq * tb;
+      }
+      const int Ge = min(op.act, P);
       uint8_t* out = reinterpret_cast<uint8_t*>(op.o0);
       const int vph = HD / 8;
       for (int v = tid; v < Hq * vph; v += 128) {
         const int h = v / vph, d0 = (v % vph) * 8;
-        const long long row = (static_cast<long long>(b) * Hq + h) * S + sq;
+        const long long f0 = base + h * T32;
+        const int nseg = llm_attn_cta_of(f0 + T32 - 1, Ge, P) - llm_attn_cta_of(f0, Ge, P) + 1;
+        const long long row0 = (static_cast<long long>(b) * Hq + h) * maxseg * S + sq;  // + seg * S
         constexpr int kMaxS = 16;
         float ms[kMaxS], ls[kMaxS];
 #pragma unroll
         for (int sp = 0; sp < kMaxS; ++sp) {
           ms[sp] = -FLT_MAX;
           ls[sp] = 0.f;
-          if (sp < splits) {
-            const float2 t = __ldcg(reinterpret_cast<const float2*>(part_ml + (sp * rows + row) * 2));
+          if (sp < nseg) {
+            const float2 t = __ldcg(reinterpret_cast<const float2*>(part_ml + (row0 + sp * S) * 2));
             ms[sp] = t.x;
             ls[sp] = t.y;
           }
@@ -668,19 +693,19 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
         for (int s0 = 0; s0 < kMaxS; s0 += 4) {
-          if (s0 >= splits) break;
+          if (s0 >= nseg) break;
           float4 x0[4], x1[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             x0[u] = x1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s0 + u < splits) {
-              const float* o = part_o + ((s0 + u) * rows + row) * HD + d0;
+            if (s0 + u < nseg) {
+              const float* o = part_o + (row0 + (s0 + u) * S) * HD + d0;
               x0[u] = ldcg_f4(o);
               x1[u] = ldcg_f4(o + 4);
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {  // split order: deterministic
+          for (int u = 0; u < 4; ++u) {  // slot order: deterministic
             const float wgt = (ls[s0 + u] > 0.f) ? exp2f(ms[s0 + u] - mx) : 0.f;
             l += ls[s0 + u] * wgt;
             acc[0] += x0[u].x * wgt; acc[1] += x0[u].y * wgt; acc[2] += x0[u].z * wgt; acc[3] += x0[u].w * wgt;
@@ -709,6 +734,7 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       return;
     }
     default: return;
+  }
   }
 }
 
@@ -1012,19 +1038,50 @@ __device__ __forceinline__ void ltile_load_async(uint8_t* tile, const __nv_bfloa
   }
 }
 
-// Flash attention of the block's S <= 64 query rows of one (sequence, q head) over a range of 64-key pages of the paged
-// cache (GQA: kv head = q head / (Hq / Hkv)); fp32 scores and softmax, P and the partial O in bf16 / fp32 like
-// bd_attn.cu. Units (split, sequence, head) are dealt round-robin to the CTAs; every unit writes its unnormalised partial
-// (O, max, sum) — the combine row op reduces the splits in a fixed order. K and V tiles are prefetched with cp.async while
-// the previous tile is in the tensor cores (mma.sync m16n8k16: this op is ~3 % of the block's time).
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention of an AR block over the paged cache, split "stream-K" style. The work is the flattened list of
+// (sequence b, q head h, 32-key half tile ht) triples — P = Hq * sum_b ceil(Sk_b / 32) of them, h-major inside a sequence so
+// that the q heads of one kv head are neighbours in time and share its pages in L2. CTA c < Ge = min(op.act, P) takes the
+// contiguous range [c P / Ge, (c + 1) P / Ge): every CTA gets the same number of half tiles (+-1) whatever the lengths
+// are, and a (b, h) block is cut into at most op.ksplit segments, one per CTA that touches it; each segment writes its
+// unnormalised partial (O, max, sum) to slot (b Hq + h) * ksplit + (c - first CTA of the block), which the combine row
+// op reduces in slot order (the same arithmetic on both sides: llm_attn_cta_of).
+// The 4 executor warps own 16 query rows each (S <= 64; Q fragments live in registers, loaded straight from global
+// memory when a block starts); K / V half tiles flow through a 3-deep cp.async ring in the A ring (one barrier per half
+// tile, loads two half tiles ahead, the page index one more ahead); fp32 scores / softmax, P in bf16, like bd_attn.cu.
+// ---------------------------------------------------------------------------------------------------------------------
+struct LlmAttnCur {
+  int b, h, ht, T32, Sk, base;  // base: flattened index of (b, 0, 0)
+};
+__device__ __forceinline__ void llm_attn_advance(LlmAttnCur& k, const int* seq_lens, int R, int S, int Hq) {
+  if (++k.ht < k.T32) return;
+  k.ht = 0;
+  if (++k.h < Hq) return;
+  k.h = 0;
+  k.base += Hq * k.T32;
+  if (++k.b < R) {
+    k.Sk = __ldcg(seq_lens + k.b) + S;
+    k.T32 = (k.Sk + 31) >> 5;
+  }
+}
 template <int HD>
-__device__ __forceinline__ void llm_attn_units(const StreamOp& op, int it, int c, int G, int tid, uint8_t* smem) {
-  const int R = op.sub, S = op.i0, Hq = op.i1, Hkv = op.i2, splits = op.ksplit, max_pages = op.N;
-  const int units = R * Hq * splits;
+__device__ __forceinline__ void htile_load_async(uint8_t* tile, const __nv_bfloat16* src, int valid_rows, int tid) {
+  constexpr int kChunks = HD / 8;
+#pragma unroll
+  for (int i0 = 0; i0 < 32 * kChunks; i0 += 128) {
+    const int i = i0 + tid;
+    const int r = i / kChunks, ch = i % kChunks;
+    const bool ok = r < valid_rows;
+    cp_async16(tile + ltile_off<HD>(r, ch), src + (ok ? r : 0) * HD + ch * 8, ok);
+  }
+}
+
+template <int HD>
+__device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int c, int tid, uint8_t* smem) {
+  constexpr int kHalf = 32 * HD * 2;  // one K (or V) half tile
+  constexpr int kStage = 2 * kHalf;
+  const int R = op.sub, S = op.i0, Hq = op.i1, Hkv = op.i2, maxseg = op.ksplit, max_pages = op.N;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + 64 * HD * 2;
-  uint8_t* sV = sK + 64 * HD * 2;
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(op.p0);
   const int* seq_lens = reinterpret_cast<const int*>(op.p1);
   const int* page_table = reinterpret_cast<const int*>(op.p2);
@@ -1033,142 +1090,171 @@ __device__ __forceinline__ void llm_attn_units(const StreamOp& op, int it, int c
   float* part_o = reinterpret_cast<float*>(op.o0);
   float* part_ml = reinterpret_cast<float*>(op.o1);
   const float scale_log2 = op.f0;
-  for (int u = c; u < units; u += G) {
-    const int h = u % Hq, b = (u / Hq) % R, split = u / (Hq * R);
-    const int hk = h / (Hq / Hkv);
-    const int Sk = __ldcg(seq_lens + b) + S;
-    const int n_tiles = (Sk + 63) / 64;
-    const int t_begin = static_cast<int>((static_cast<long long>(split) * n_tiles) / splits);
-    const int t_end = static_cast<int>((static_cast<long long>(split + 1) * n_tiles) / splits);
-    float o_acc[HD / 8][4];
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
-    float m_run[2] = {-FLT_MAX, -FLT_MAX}, l_run[2] = {0.f, 0.f};
-    auto kv_src = [&](const __nv_bfloat16* pool, int kt) {
-      const int page = page_table[b * max_pages + kt];
-      return pool + (static_cast<long long>(page) * Hkv + hk) * 64 * HD;
-    };
-    epi_bar();  // the previous unit's tiles are dead
-    if (t_begin < t_end) {
-      ltile_load_async<HD>(sQ, q + (static_cast<long long>(b) * S) * Hq * HD + static_cast<long long>(h) * HD,
-                           static_cast<long long>(Hq) * HD, S, tid);
-      ltile_load_async<HD>(sK, kv_src(kpool, t_begin), HD, min(64, Sk - t_begin * 64), tid);
-      cp_async_commit();
-      ltile_load_async<HD>(sV, kv_src(vpool, t_begin), HD, min(64, Sk - t_begin * 64), tid);
-      cp_async_commit();
-    }
-    for (int kt = t_begin; kt < t_end; ++kt) {
-      const int k0 = kt * 64;
-      cp_async_wait<1>();  // Q + K(kt) landed (V(kt) may still be in flight)
-      epi_bar();
-      float sc[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ks += 2) {
-        uint32_t a0[4], a1[4];
-        s_ldmatrix_x4(a0, smem_u32(sQ + ltile_off<HD>(warp * 16 + (lane & 15), 2 * ks + (lane >> 4))));
-        s_ldmatrix_x4(a1, smem_u32(sQ + ltile_off<HD>(warp * 16 + (lane & 15), 2 * ks + 2 + (lane >> 4))));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint32_t bk[4];
-          s_ldmatrix_x4(bk, smem_u32(sK + ltile_off<HD>(8 * j + (lane & 7), 2 * ks + (lane >> 3))));
-          s_mma_16816(sc[j], a0, bk[0], bk[1]);
-          s_mma_16816(sc[j], a1, bk[2], bk[3]);
-        }
+  int P = 0;
+  for (int b = 0; b < R; ++b) P += Hq * ((__ldcg(seq_lens + b) + S + 31) >> 5);
+  const int Ge = min(op.act, P);
+  if (c >= Ge) return;
+  const int lo = static_cast<int>(static_cast<long long>(c) * P / Ge);
+  const int hi = static_cast<int>(static_cast<long long>(c + 1) * P / Ge);
+  LlmAttnCur cu;  // compute cursor
+  {
+    int base = 0;
+    for (int b = 0;; ++b) {
+      const int Sk = __ldcg(seq_lens + b) + S, T32 = (Sk + 31) >> 5;
+      if (lo - base < Hq * T32 || b == R - 1) {
+        cu = LlmAttnCur{b, (lo - base) / T32, (lo - base) % T32, T32, Sk, base};
+        break;
       }
-      epi_bar();  // every warp is done with K(kt): fetch K(kt + 1) behind the softmax and P V of this tile
-      if (kt + 1 < t_end) ltile_load_async<HD>(sK, kv_src(kpool, kt + 1), HD, min(64, Sk - (kt + 1) * 64), tid);
-      cp_async_commit();
-      float m_new[2] = {m_run[0], m_run[1]};
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int key = k0 + 8 * j + 2 * t + (i & 1);
-          const float v = key < Sk ? sc[j][i] * scale_log2 : -FLT_MAX;
-          sc[j][i] = v;
-          m_new[i >> 1] = fmaxf(m_new[i >> 1], v);
-        }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
-        m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
-      }
-      float corr[2], l_add[2] = {0.f, 0.f};
-#pragma unroll
-      for (int r = 0; r < 2; ++r) corr[r] = exp2f(m_run[r] - m_new[r]);
-      uint32_t pa[4][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float e[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          e[i] = (sc[j][i] == -FLT_MAX) ? 0.f : exp2f(sc[j][i] - m_new[i >> 1]);
-          l_add[i >> 1] += e[i];
-        }
-        const int kk = j >> 1;
-        if ((j & 1) == 0) {
-          pa[kk][0] = s_pack_bf16(e[0], e[1]);
-          pa[kk][1] = s_pack_bf16(e[2], e[3]);
-        } else {
-          pa[kk][2] = s_pack_bf16(e[0], e[1]);
-          pa[kk][3] = s_pack_bf16(e[2], e[3]);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        l_run[r] = l_run[r] * corr[r] + l_add[r];
-        m_run[r] = m_new[r];
-      }
-#pragma unroll
-      for (int n = 0; n < HD / 8; ++n) {
-        o_acc[n][0] *= corr[0];
-        o_acc[n][1] *= corr[0];
-        o_acc[n][2] *= corr[1];
-        o_acc[n][3] *= corr[1];
-      }
-      cp_async_wait<1>();  // V(kt) landed (K(kt + 1) may still be in flight)
-      epi_bar();
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-        for (int n = 0; n < HD / 8; n += 2) {
-          uint32_t bv[4];
-          s_ldmatrix_x4_trans(bv, smem_u32(sV + ltile_off<HD>(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), n + (lane >> 4))));
-          s_mma_16816(o_acc[n], pa[kk], bv[0], bv[1]);
-          s_mma_16816(o_acc[n + 1], pa[kk], bv[2], bv[3]);
-        }
-      }
-      epi_bar();  // every warp is done with V(kt)
-      if (kt + 1 < t_end) ltile_load_async<HD>(sV, kv_src(vpool, kt + 1), HD, min(64, Sk - (kt + 1) * 64), tid);
-      cp_async_commit();
-    }
-    cp_async_wait<0>();
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
-      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int qrow = warp * 16 + g + 8 * r;
-      if (qrow >= S) continue;
-      const long long row = ((static_cast<long long>(split) * R + b) * Hq + h) * S + qrow;
-      float* o = part_o + row * HD;
-#pragma unroll
-      for (int n = 0; n < HD / 8; ++n)
-        *reinterpret_cast<float2*>(o + 8 * n + 2 * t) = make_float2(o_acc[n][2 * r], o_acc[n][2 * r + 1]);
-      if (t == 0) {
-        part_ml[row * 2] = m_run[r];
-        part_ml[row * 2 + 1] = l_run[r];
-      }
+      base += Hq * T32;
     }
   }
+  LlmAttnCur ld = cu;  // load cursor, two half tiles ahead
+  int f_ld = lo;
+  int pg = __ldg(page_table + ld.b * max_pages + (ld.ht >> 1));
+  auto issue = [&](int buf) {
+    if (f_ld < hi) {
+      const int hk = ld.h / (Hq / Hkv);
+      const long long off = ((static_cast<long long>(pg) * Hkv + hk) * 64 + (ld.ht & 1) * 32) * HD;
+      const int valid = min(32, ld.Sk - ld.ht * 32);
+      uint8_t* dst = smem + buf * kStage;
+      htile_load_async<HD>(dst, kpool + off, valid, tid);
+      htile_load_async<HD>(dst + kHalf, vpool + off, valid, tid);
+      llm_attn_advance(ld, seq_lens, R, S, Hq);
+      if (++f_ld < hi) pg = __ldg(page_table + ld.b * max_pages + (ld.ht >> 1));  // consumed one half tile later
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  uint32_t qf[HD / 16][4];
+  float o_acc[HD / 8][4];
+  float m_run[2], l_run[2];
+  bool fresh = true;
+  const int n_st = hi - lo;
+  for (int i = 0; i < n_st; ++i) {
+    if (fresh) {  // a (b, h) block starts (or continues from another CTA): Q fragments, empty accumulators
+      fresh = false;
+      const __nv_bfloat16* qb = q + (static_cast<long long>(cu.b) * S * Hq + cu.h) * HD;
+      const int r0 = warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        const int col = 16 * ks + 2 * t;
+        const unsigned int* p0 = reinterpret_cast<const unsigned int*>(qb + static_cast<long long>(r0) * Hq * HD + col);
+        const unsigned int* p1 = reinterpret_cast<const unsigned int*>(qb + static_cast<long long>(r1) * Hq * HD + col);
+        qf[ks][0] = r0 < S ? __ldcg(p0) : 0u;
+        qf[ks][1] = r1 < S ? __ldcg(p1) : 0u;
+        qf[ks][2] = r0 < S ? __ldcg(p0 + 4) : 0u;
+        qf[ks][3] = r1 < S ? __ldcg(p1 + 4) : 0u;
+      }
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o_acc[n][j] = 0.f;
+      m_run[0] = m_run[1] = -FLT_MAX;
+      l_run[0] = l_run[1] = 0.f;
+    }
+    cp_async_wait<1>();  // half tile i landed (i + 1 may still be in flight)
+    epi_bar();           // ... for every thread's share, and every warp is done with half tile i - 1
+    issue((i + 2) % 3);  // refill the buffer half tile i - 1 used
+    const uint8_t* sK = smem + (i % 3) * kStage;
+    const uint8_t* sV = sK + kHalf;
+    const int k0 = cu.ht * 32;
+    float sc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ks += 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t bk[4];
+        s_ldmatrix_x4(bk, smem_u32(sK + ltile_off<HD>(8 * j + (lane & 7), 2 * ks + (lane >> 3))));
+        s_mma_16816(sc[j], qf[ks], bk[0], bk[1]);
+        s_mma_16816(sc[j], qf[ks + 1], bk[2], bk[3]);
+      }
+    }
+    float m_new[2] = {m_run[0], m_run[1]};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = k0 + 8 * j + 2 * t + (e & 1);
+        const float v = key < cu.Sk ? sc[j][e] * scale_log2 : -FLT_MAX;
+        sc[j][e] = v;
+        m_new[e >> 1] = fmaxf(m_new[e >> 1], v);
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
+      m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
+    }
+    float corr[2], l_add[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) corr[r] = exp2f(m_run[r] - m_new[r]);
+    uint32_t pa[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float e[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        e[x] = (sc[j][x] == -FLT_MAX) ? 0.f : exp2f(sc[j][x] - m_new[x >> 1]);
+        l_add[x >> 1] += e[x];
+      }
+      const int kk = j >> 1;
+      if ((j & 1) == 0) {
+        pa[kk][0] = s_pack_bf16(e[0], e[1]);
+        pa[kk][1] = s_pack_bf16(e[2], e[3]);
+      } else {
+        pa[kk][2] = s_pack_bf16(e[0], e[1]);
+        pa[kk][3] = s_pack_bf16(e[2], e[3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] = l_run[r] * corr[r] + l_add[r];
+      m_run[r] = m_new[r];
+    }
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      o_acc[n][0] *= corr[0];
+      o_acc[n][1] *= corr[0];
+      o_acc[n][2] *= corr[1];
+      o_acc[n][3] *= corr[1];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+      for (int n = 0; n < HD / 8; n += 2) {
+        uint32_t bv[4];
+        s_ldmatrix_x4_trans(bv, smem_u32(sV + ltile_off<HD>(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), n + (lane >> 4))));
+        s_mma_16816(o_acc[n], pa[kk], bv[0], bv[1]);
+        s_mma_16816(o_acc[n + 1], pa[kk], bv[2], bv[3]);
+      }
+    }
+    if (cu.ht == cu.T32 - 1 || i == n_st - 1) {  // the block (or this CTA's share of it) ends: store the segment
+      fresh = true;
+      const int hb = cu.b * Hq + cu.h;
+      const int seg = c - llm_attn_cta_of(cu.base + cu.h * cu.T32, Ge, P);
+      if (seg < 0 || seg >= maxseg) __trap();
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float l = l_run[r];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const int qrow = warp * 16 + g + 8 * r;
+        if (qrow >= S) continue;
+        const long long row = (static_cast<long long>(hb) * maxseg + seg) * S + qrow;
+        float* o = part_o + row * HD;
+#pragma unroll
+        for (int n = 0; n < HD / 8; ++n)
+          *reinterpret_cast<float2*>(o + 8 * n + 2 * t) = make_float2(o_acc[n][2 * r], o_acc[n][2 * r + 1]);
+        if (t == 0) *reinterpret_cast<float2*>(part_ml + row * 2) = make_float2(m_run[r], l);
+      }
+    }
+    llm_attn_advance(cu, seq_lens, R, S, Hq);
+  }
+  cp_async_wait<0>();
   epi_bar();
 }
 
@@ -1281,7 +1367,7 @@ __device__ __forceinline__ const void* tab_ptr(const StreamOp& op, int it, int s
 // scr_free, and resumes only after the executors signal scr_done.
 __device__ __forceinline__ bool op_uses_scratch(const StreamProgram& prog, const StreamOp& op, int c) {
   if (op.kind == kOpAttn) return c < (prog.M / op.i0) * (op.N / op.K);
-  if (op.kind == kOpLlmAttn) return c < op.sub * op.i1 * op.ksplit;
+  if (op.kind == kOpLlmAttn) return c < op.act;
   return op.kind == kOpRow && op.sub == kRowFinal && c < prog.M;
 }
 
@@ -1360,6 +1446,7 @@ __device__ __forceinline__ unsigned int wait_target(int wait_prev, unsigned int 
     if (prog.dbg && (q_) < prog.dbg_ops) prog.dbg[(static_cast<long long>(q_) * G + c) * 8 + (e_)] = gtimer(); \
   } while (0)
 
+template <int FAM>
 __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __grid_constant__ StreamProgram prog) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1662,14 +1749,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         const bool scratch = op_uses_scratch(prog, op, c);
         if (scratch) mbar_wait(scr_free, scr_uses & 1u);  // the A ring is ours (see op_uses_scratch)
         if (op.kind == kOpRow) {
-          row_op(prog, op, it, c, tid, red, smem_a);
-        } else if (op.kind == kOpLlmRope) {
-          if (op.K == 128) llm_rope_append<128>(op, it, c, G, tid);
-          else llm_rope_append<64>(op, it, c, G, tid);
-        } else if (op.kind == kOpLlmAttn) {
-          if (op.K == 128) llm_attn_units<128>(op, it, c, G, tid, smem_a);
-          else llm_attn_units<64>(op, it, c, G, tid, smem_a);
-        } else {
+          row_op<FAM>(prog, op, it, c, tid, red, smem_a);
+        } else if constexpr (FAM == kStreamFamLlm) {
+          if (op.kind == kOpLlmRope) {
+            if (op.K == 128) llm_rope_append<128>(op, it, c, G, tid);
+            else llm_rope_append<64>(op, it, c, G, tid);
+          } else if (op.kind == kOpLlmAttn && c < op.act) {
+            if (op.K == 128) llm_attn_stream<128>(op, it, c, tid, smem_a);
+            else llm_attn_stream<64>(op, it, c, tid, smem_a);
+          }
+        } else if (op.kind == kOpAttn) {
           const int units = (prog.M / op.i0) * (op.N / op.K);
           if (c < units) {
             if (op.K == 128) attn_unit<128>(op, c, tid, smem_a, aux_bar, aux_uses & 1u);
@@ -1776,7 +1865,10 @@ int stream_launch(const StreamProgram& prog_in, cudaStream_t stream) {
     int dev = 0;
     BD_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      BD_CUDA_TRY(cudaFuncSetAttribute(bd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamSmem::kTotal));
+      BD_CUDA_TRY(cudaFuncSetAttribute(bd_stream_kernel<kStreamFamHead>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       StreamSmem::kTotal));
+      BD_CUDA_TRY(cudaFuncSetAttribute(bd_stream_kernel<kStreamFamLlm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       StreamSmem::kTotal));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -1792,7 +1884,9 @@ int stream_launch(const StreamProgram& prog_in, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ++g_launch_count;
-  BD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bd_stream_kernel, prog));
+  BD_REQUIRE(prog.family == kStreamFamHead || prog.family == kStreamFamLlm);
+  if (prog.family == kStreamFamLlm) BD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bd_stream_kernel<kStreamFamLlm>, prog));
+  else BD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bd_stream_kernel<kStreamFamHead>, prog));
   return BD_OK;
 }
 

@@ -116,7 +116,10 @@ struct StreamOp {
 };
 constexpr int kTabSlots = 8;
 
+enum : int { kStreamFamHead = 0, kStreamFamLlm = 1 };  // which instance of the kernel runs the program (its executors)
+
 struct StreamProgram {
+  int family;
   int n_pre, n_body, n_iter, n_post;
   int M;          // token rows (<= 128)
   int n_ctas;

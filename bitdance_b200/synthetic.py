@@ -41,11 +41,13 @@ def _gpu_state_dict(spec: dict, seed: int, device, std=0.02) -> dict:
             for k, v in spec.items()}
 
 
-def build_synthetic_engine(model: str = "BitDance-14B-64x", device="cuda", seed: int = 0, with_ae: bool = True):
-    """Returns (engine, embed_table bf16 [vocab, D])."""
+def build_synthetic_engine(model: str = "BitDance-14B-64x", device="cuda", seed: int = 0, with_ae: bool = True,
+                           llm_stream: bool | None = None):
+    """Returns (engine, embed_table bf16 [vocab, D]). llm_stream: also keep the stream-major copy of the decoder weights so
+    that an AR block runs as ONE persistent launch (None: the BD_LLM_STREAM environment variable, default off)."""
     m = MODELS[model]
     dev = torch.device(device)
-    llm = LlmRunner(None, m["llm"], device=dev, synthetic_seed=seed + 1)
+    llm = LlmRunner(None, m["llm"], device=dev, synthetic_seed=seed + 1, stream=llm_stream)
     hc = m["head"]
     sd_head = _gpu_state_dict(head_spec(hc["ch_target"], hc["ch_cond"], hc["ch_latent"], hc["depth_latent"],
                                         hc["depth_adanln"], hc["use_swiglu"]), seed + 2, dev)
