@@ -923,7 +923,10 @@ __device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int 
   __nv_bfloat16* vpool = kpool + op.l1;
   const long long tasks = static_cast<long long>(M) * heads;
   const long long stride = static_cast<long long>(G) * 4;
-  constexpr int U = 4;  // tasks in flight per warp: a task is a chain of ~4 dependent L2 round trips, 12 tasks per warp
+  constexpr int U = 6;  // tasks in flight per warp (12 tasks per warp at the 14B shape): two rounds of one L2 round trip
+  // the sequence lengths once per warp (lane b holds sequence b's; more than 32 sequences: read per task)
+  const int R = op.sub;
+  const int len_lane = (lane < R) ? __ldcg(seq_lens + lane) : 0;
   for (long long gw0 = static_cast<long long>(c) * 4 + warp; gw0 < tasks; gw0 += stride * U) {
     float x[U][VPT], cs[U][VPT], sn[U][VPT];
     int pos[U], page[U];
@@ -939,7 +942,7 @@ __device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int 
       if (!live[u]) continue;
       const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
       const int b = m / S, sidx = m % S;
-      pos[u] = __ldcg(seq_lens + b) + sidx;
+      pos[u] = (R <= 32 ? __shfl_sync(0xffffffffu, len_lane, b) : __ldcg(seq_lens + b)) + sidx;
       if (pos[u] < 0 || pos[u] >= max_pages * 64) {
         if (lane == 0) printf("bd_stream: sequence %d position %d outside the KV cache (%d tokens)\n", b, pos[u], max_pages * 64);
         __trap();
