@@ -14,7 +14,7 @@ FULL="python bench.py --steps 1 --warmup 0 --ar-steps 64 --graph 1 --no-cpu-base
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NLAUNCH:-4000} --csv \
     --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/${TAG}_launches.csv)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:bd_stream_kernel -c 2 -f \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:bd_stream_kernel -c 3 -f \
     -o gpurun_out/${TAG}_prof_stream $BENCH > gpurun_out/${TAG}_ncu_stream.log 2>&1
 echo "stream capture rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_gemm_kernel -s 4 -c 3 -f \
@@ -27,4 +27,9 @@ echo "attn capture rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_conv_kernel -s 20 -c 3 -f \
     -o gpurun_out/${TAG}_prof_conv python scripts/ae_bench.py --bs 1 --reps 1 > gpurun_out/${TAG}_ncu_conv.log 2>&1
 echo "conv capture rc=$?"
+# ImageNet class-conditional path (B-16x, bs 64): launch list of the first AR positions
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv \
+    --log-file gpurun_out/${TAG}_imagenet_launches.csv python scripts/imagenet_bench.py --bs 64 --reps 1 --no-warmup \
+    > gpurun_out/${TAG}_ncu_imagenet.log 2>&1
+echo "imagenet launch list rc=$?"
 ls -la gpurun_out/${TAG}_prof_*.ncu-rep 2>/dev/null

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--cfg", type=float, default=3.9)
     ap.add_argument("--latent-dim", type=int, default=32)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--no-warmup", action="store_true", help="profiling (ncu launch list): no warm-up pass")
     args = ap.parse_args()
     dev = torch.device("cuda")
     cfg = dict(MODELS[args.model], latent_dim=args.latent_dim, down_size=16, patch_size=1, resolution=256, cls_token_num=64,
@@ -47,7 +48,8 @@ def main():
     hw, pn = eng.h * eng.w, eng.pn
     for bs in args.bs:
         ids = torch.randint(0, 1000, (bs,), device=dev)
-        eng.sample_tokens(ids, args.steps, args.cfg)   # warm-up (allocations, first launches)
+        if not args.no_warmup:
+            eng.sample_tokens(ids, args.steps, args.cfg)   # warm-up (allocations, first launches)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
