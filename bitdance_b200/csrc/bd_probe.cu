@@ -81,6 +81,38 @@ __global__ void __launch_bounds__(96, 1) probe_stream_kernel(ProbeArgs a) {
   }
 }
 
+// Issue rate of the legacy tensor path (mma.sync.m16n8k16 bf16 -> HMMA) with few warps per SM sub-partition: CH independent
+// accumulator chains per warp, `iters` rounds; per-warp cycles -> out[cta * warps + warp]. (The in-engine attention runs on
+// 4 executor warps: is it bound by HMMA issue, and would more warps or more chains help?)
+template <int CH>
+__global__ void probe_hmma_kernel(int iters, long long* out, float* sink) {
+  float acc[CH][4];
+  uint32_t a[4], b[2];
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = 0x3c003c00u + threadIdx.x + j;
+  b[0] = 0x38003800u + threadIdx.x;
+  b[1] = 0x34003400u;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
+                   : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) s += acc[c][0] + acc[c][1] + acc[c][2] + acc[c][3];
+  if (s == 123.456f) sink[0] = s;
+  if ((threadIdx.x & 31) == 0) out[blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)] = t1 - t0;
+}
+
 }  // namespace bd
 
 using namespace bd;
@@ -97,6 +129,22 @@ extern "C" int bd_probe_stream(const void* w, long long w_per_cta, int w_chunk, 
   ProbeArgs a{static_cast<const uint8_t*>(w), w_per_cta, w_chunk, w_stages, static_cast<const uint8_t*>(x), x_bytes,
               x_chunk, x_stages};
   probe_stream_kernel<<<n_ctas, 96, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  BD_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+extern "C" int bd_probe_hmma(int warps, int chains, int iters, int n_ctas, long long* out_cycles, float* sink,
+                             bd_stream_t stream) {
+  BD_REQUIRE(warps >= 1 && warps <= 32 && iters > 0 && n_ctas > 0 && out_cycles && sink);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (chains) {
+    case 1: probe_hmma_kernel<1><<<n_ctas, warps * 32, 0, st>>>(iters, out_cycles, sink); break;
+    case 2: probe_hmma_kernel<2><<<n_ctas, warps * 32, 0, st>>>(iters, out_cycles, sink); break;
+    case 4: probe_hmma_kernel<4><<<n_ctas, warps * 32, 0, st>>>(iters, out_cycles, sink); break;
+    case 8: probe_hmma_kernel<8><<<n_ctas, warps * 32, 0, st>>>(iters, out_cycles, sink); break;
+    case 16: probe_hmma_kernel<16><<<n_ctas, warps * 32, 0, st>>>(iters, out_cycles, sink); break;
+    default: return BD_ERR_INVALID;
+  }
   BD_LAUNCH_CHECK();
   return BD_OK;
 }

@@ -658,11 +658,11 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       const float* part_o = reinterpret_cast<const float*>(op.p0);
       const float* part_ml = reinterpret_cast<const float*>(op.p1);
       const int* seq_lens = reinterpret_cast<const int*>(op.p2);
-      int P = 0, base = 0, T32 = 0;
+      int P = 0, base = 0, Tb = 0;
       for (int bb = 0; bb < R; ++bb) {
-        const int tb = (__ldcg(seq_lens + bb) + S + 31) >> 5;
+        const int tb = (__ldcg(seq_lens + bb) + S + 63) >> 6;
         if (bb < b) base += Hq * tb;
-        if (bb == b) T32 = tb;
+        if (bb == b) Tb = tb;
         P += Hq * tb;
       }
       const int Ge = min(op.act, P);
@@ -670,8 +670,8 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       const int vph = HD / 8;
       for (int v = tid; v < Hq * vph; v += 128) {
         const int h = v / vph, d0 = (v % vph) * 8;
-        const long long f0 = base + h * T32;
-        const int nseg = llm_attn_cta_of(f0 + T32 - 1, Ge, P) - llm_attn_cta_of(f0, Ge, P) + 1;
+        const long long f0 = base + h * Tb;
+        const int nseg = llm_attn_cta_of(f0 + Tb - 1, Ge, P) - llm_attn_cta_of(f0, Ge, P) + 1;
         const long long row0 = (static_cast<long long>(b) * Hq + h) * maxseg * S + sq;  // + seg * S
         constexpr int kMaxS = 16;
         float ms[kMaxS], ls[kMaxS];
@@ -756,6 +756,12 @@ __device__ __forceinline__ void s_mma_16816(float (&c)[4], const uint32_t (&a)[4
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// mma.sync without `volatile`: a pure register operation the compiler may schedule freely between the loads
+__device__ __forceinline__ void s_mma_16816_nv(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ uint32_t s_pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -815,13 +821,15 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
     uint32_t a0[4], a1[4];
     s_ldmatrix_x4(a0, smem_u32(sQ + s_tile_off(warp * 16 + (lane & 15), 2 * ks + (lane >> 4), row0)));
     s_ldmatrix_x4(a1, smem_u32(sQ + s_tile_off(warp * 16 + (lane & 15), 2 * ks + 2 + (lane >> 4), row0)));
+    // the 8 key blocks are 8 independent accumulator chains: all loads first, then the two k-steps chain by chain (the mma
+    // is a plain register operation, free to be scheduled; per accumulator the order of the k-steps is unchanged)
+    uint32_t bk[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t bk[4];
-      s_ldmatrix_x4(bk, smem_u32(sK + s_tile_off(8 * j + (lane & 7), 2 * ks + (lane >> 3), row0)));
-      s_mma_16816(s[j], a0, bk[0], bk[1]);
-      s_mma_16816(s[j], a1, bk[2], bk[3]);
-    }
+    for (int j = 0; j < 8; ++j) s_ldmatrix_x4(bk[j], smem_u32(sK + s_tile_off(8 * j + (lane & 7), 2 * ks + (lane >> 3), row0)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_mma_16816_nv(s[j], a0, bk[j][0], bk[j][1]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_mma_16816_nv(s[j], a1, bk[j][2], bk[j][3]);
   }
   float mx[2] = {-FLT_MAX, -FLT_MAX};
 #pragma unroll
@@ -865,11 +873,17 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-    for (int n = 0; n < HD / 8; n += 2) {
-      uint32_t bv[4];
-      s_ldmatrix_x4_trans(bv, smem_u32(sV + s_tile_off(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), n + (lane >> 4), row0)));
-      s_mma_16816(o_acc[n], pa[kk], bv[0], bv[1]);
-      s_mma_16816(o_acc[n + 1], pa[kk], bv[2], bv[3]);
+    for (int nh = 0; nh < HD / 8; nh += 8) {
+      uint32_t bv[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+        s_ldmatrix_x4_trans(bv[n], smem_u32(sV + s_tile_off(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1),
+                                                            nh + 2 * n + (lane >> 4), row0)));
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        s_mma_16816_nv(o_acc[nh + 2 * n], pa[kk], bv[n][0], bv[n][1]);
+        s_mma_16816_nv(o_acc[nh + 2 * n + 1], pa[kk], bv[n][2], bv[n][3]);
+      }
     }
   }
 #pragma unroll
@@ -943,10 +957,7 @@ __device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int 
       const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
       const int b = m / S, sidx = m % S;
       pos[u] = (R <= 32 ? __shfl_sync(0xffffffffu, len_lane, b) : __ldcg(seq_lens + b)) + sidx;
-      if (pos[u] < 0 || pos[u] >= max_pages * 64) {
-        if (lane == 0) printf("bd_stream: sequence %d position %d outside the KV cache (%d tokens)\n", b, pos[u], max_pages * 64);
-        __trap();
-      }
+      if (pos[u] < 0 || pos[u] >= max_pages * 64) __trap();  // outside the KV cache (the host checks the bound too)
       const __nv_bfloat16* src = qkv + static_cast<long long>(m) * heads * HD + static_cast<long long>(hh) * HD + lane * VPT;
       if constexpr (VPT == 4) {
         const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(src));
@@ -960,10 +971,17 @@ __device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int 
       }
       if (hh >= Hq) page[u] = __ldg(page_table + b * max_pages + pos[u] / 64);
       if (hh < Hq + Hkv) {
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) {
-          cs[u][j] = __ldg(rope_cos + static_cast<long long>(pos[u]) * HD + lane * VPT + j);
-          sn[u][j] = __ldg(rope_sin + static_cast<long long>(pos[u]) * HD + lane * VPT + j);
+        const long long ro = static_cast<long long>(pos[u]) * HD + lane * VPT;
+        if constexpr (VPT == 4) {
+          const float4 cv = __ldg(reinterpret_cast<const float4*>(rope_cos + ro));
+          const float4 sv = __ldg(reinterpret_cast<const float4*>(rope_sin + ro));
+          cs[u][0] = cv.x; cs[u][1] = cv.y; cs[u][2] = cv.z; cs[u][3] = cv.w;
+          sn[u][0] = sv.x; sn[u][1] = sv.y; sn[u][2] = sv.z; sn[u][3] = sv.w;
+        } else {
+          const float2 cv = __ldg(reinterpret_cast<const float2*>(rope_cos + ro));
+          const float2 sv = __ldg(reinterpret_cast<const float2*>(rope_sin + ro));
+          cs[u][0] = cv.x; cs[u][1] = cv.y;
+          sn[u][0] = sv.x; sn[u][1] = sv.y;
         }
       }
     }
@@ -1043,58 +1061,97 @@ __device__ __forceinline__ void ltile_load_async(uint8_t* tile, const __nv_bfloa
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Attention of an AR block over the paged cache, split "stream-K" style. The work is the flattened list of
-// (sequence b, q head h, 32-key half tile ht) triples — P = Hq * sum_b ceil(Sk_b / 32) of them, h-major inside a sequence so
+// (sequence b, q head h, 64-key tile kt) triples — P = Hq * sum_b ceil(Sk_b / 64) of them, h-major inside a sequence so
 // that the q heads of one kv head are neighbours in time and share its pages in L2. CTA c < Ge = min(op.act, P) takes the
-// contiguous range [c P / Ge, (c + 1) P / Ge): every CTA gets the same number of half tiles (+-1) whatever the lengths
-// are, and a (b, h) block is cut into at most op.ksplit segments, one per CTA that touches it; each segment writes its
-// unnormalised partial (O, max, sum) to slot (b Hq + h) * ksplit + (c - first CTA of the block), which the combine row
-// op reduces in slot order (the same arithmetic on both sides: llm_attn_cta_of).
-// The 4 executor warps own 16 query rows each (S <= 64; Q fragments live in registers, loaded straight from global
-// memory when a block starts); K / V half tiles flow through a 3-deep cp.async ring in the A ring (one barrier per half
-// tile, loads two half tiles ahead, the page index one more ahead); fp32 scores / softmax, P in bf16, like bd_attn.cu.
+// contiguous range [c P / Ge, (c + 1) P / Ge): every CTA gets the same number of tiles (+-1) whatever the lengths are (they
+// are device data: no host planning, one captured graph for every step of an image), and a (b, h) block is cut into at
+// most op.ksplit segments, one per CTA that touches it; each segment writes its unnormalised partial (O, max, sum) to slot
+// (b Hq + h) * ksplit + (c - first CTA of the block), which the combine row op reduces in slot order (the same arithmetic
+// on both sides: llm_attn_cta_of).
+// The 4 executor warps own 16 query rows each (S <= 64; Q fragments live in registers, loaded straight from global memory
+// when a block starts); K / V tiles are double-buffered in the A ring with cp.async (one barrier per tile, the next tile
+// and the page index after it in flight); fp32 scores / softmax, P in bf16, like bd_attn.cu.
+// The op is bound by instruction issue — one warp per scheduler, so nothing hides a dependent instruction's latency
+// (measured: no time waiting for K/V; profiles/r02_llm_timeline.txt) — hence: per-lane shared-memory offsets and the cp.async
+// source / destination offsets are computed once per op; key masking only in the last tile of a sequence; one FFMA + ex2 per
+// score; the accumulator rescale is skipped when no row maximum of the warp moved; independent mma chains are interleaved.
 // ---------------------------------------------------------------------------------------------------------------------
 struct LlmAttnCur {
-  int b, h, ht, T32, Sk, base;  // base: flattened index of (b, 0, 0)
+  int b, h, kt, T, Sk, base;  // base: flattened index of (b, 0, 0)
+  int hk, hg;                 // kv head of h, position of h in its group
 };
-__device__ __forceinline__ void llm_attn_advance(LlmAttnCur& k, const int* seq_lens, int R, int S, int Hq) {
-  if (++k.ht < k.T32) return;
-  k.ht = 0;
+__device__ __forceinline__ void llm_attn_advance(LlmAttnCur& k, const int* seq_lens, int R, int S, int Hq, int gqa) {
+  if (++k.kt < k.T) return;
+  k.kt = 0;
+  if (++k.hg == gqa) {
+    k.hg = 0;
+    ++k.hk;
+  }
   if (++k.h < Hq) return;
   k.h = 0;
-  k.base += Hq * k.T32;
+  k.hk = 0;
+  k.base += Hq * k.T;
   if (++k.b < R) {
     k.Sk = __ldcg(seq_lens + k.b) + S;
-    k.T32 = (k.Sk + 31) >> 5;
+    k.T = (k.Sk + 63) >> 6;
   }
 }
-template <int HD>
-__device__ __forceinline__ void htile_load_async(uint8_t* tile, const __nv_bfloat16* src, int valid_rows, int tid) {
-  constexpr int kChunks = HD / 8;
-#pragma unroll
-  for (int i0 = 0; i0 < 32 * kChunks; i0 += 128) {
-    const int i = i0 + tid;
-    const int r = i / kChunks, ch = i % kChunks;
-    const bool ok = r < valid_rows;
-    cp_async16(tile + ltile_off<HD>(r, ch), src + (ok ? r : 0) * HD + ch * 8, ok);
-  }
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_sz(uint32_t smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// The op descriptor is a copy of a kernel parameter: left alone, the compiler re-reads its fields from the constant bank
+// with a run-time index wherever they are used (an IMAD + LDC chain in front of every use in the tile loop). pin() makes
+// the value opaque, so it stays in a register.
+__device__ __forceinline__ int pin(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ long long pin(long long v) {
+  asm volatile("" : "+l"(v));
+  return v;
+}
+__device__ __forceinline__ float pin(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T* pin(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
 }
 
 template <int HD>
-__device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int c, int tid, uint8_t* smem) {
-  constexpr int kHalf = 32 * HD * 2;  // one K (or V) half tile
-  constexpr int kStage = 2 * kHalf;
-  const int R = op.sub, S = op.i0, Hq = op.i1, Hkv = op.i2, maxseg = op.ksplit, max_pages = op.N;
+__device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int c, int tid, uint8_t* smem, int dbg_mode,
+                                                unsigned long long* dbg_slot) {
+  constexpr int kTile = 64 * HD * 2;  // one K (or V) tile
+  constexpr int kStage = 2 * kTile;
+  constexpr int kChunks = HD / 8;     // 16-byte chunks per row
+  constexpr int kCopies = 64 * kChunks / 128;  // cp.async per thread per tile
+  constexpr int kRowStep = 128 / kChunks;      // rows between two copies of a thread
+  static_assert(kRowStep % 8 == 0, "the swizzle phase of a thread's rows must be constant");
+  const int R = pin(op.sub), S = pin(op.i0), Hq = pin(op.i1), Hkv = pin(op.i2), maxseg = op.ksplit, max_pages = pin(op.N);
+  const int gqa = pin(Hq / Hkv);
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(op.p0);
-  const int* seq_lens = reinterpret_cast<const int*>(op.p1);
-  const int* page_table = reinterpret_cast<const int*>(op.p2);
-  const __nv_bfloat16* kpool = reinterpret_cast<const __nv_bfloat16*>(op.p3) + static_cast<long long>(it) * op.l0;
-  const __nv_bfloat16* vpool = kpool + op.l1;
+  const int* seq_lens = pin(reinterpret_cast<const int*>(op.p1));
+  const int* page_table = pin(reinterpret_cast<const int*>(op.p2));
+  const __nv_bfloat16* kpool = pin(reinterpret_cast<const __nv_bfloat16*>(op.p3) + static_cast<long long>(it) * op.l0);
+  const long long v_off = pin(op.l1);
   float* part_o = reinterpret_cast<float*>(op.o0);
   float* part_ml = reinterpret_cast<float*>(op.o1);
-  const float scale_log2 = op.f0;
+  const float scale_log2 = pin(op.f0);
   int P = 0;
-  for (int b = 0; b < R; ++b) P += Hq * ((__ldcg(seq_lens + b) + S + 31) >> 5);
+  for (int b = 0; b < R; ++b) P += Hq * ((__ldcg(seq_lens + b) + S + 63) >> 6);
   const int Ge = min(op.act, P);
   if (c >= Ge) return;
   const int lo = static_cast<int>(static_cast<long long>(c) * P / Ge);
@@ -1103,35 +1160,63 @@ __device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int 
   {
     int base = 0;
     for (int b = 0;; ++b) {
-      const int Sk = __ldcg(seq_lens + b) + S, T32 = (Sk + 31) >> 5;
-      if (lo - base < Hq * T32 || b == R - 1) {
-        cu = LlmAttnCur{b, (lo - base) / T32, (lo - base) % T32, T32, Sk, base};
+      const int Sk = __ldcg(seq_lens + b) + S, T = (Sk + 63) >> 6;
+      if (lo - base < Hq * T || b == R - 1) {
+        const int h = (lo - base) / T;
+        cu = LlmAttnCur{b, h, (lo - base) % T, T, Sk, base, h / gqa, h % gqa};
         break;
       }
-      base += Hq * T32;
+      base += Hq * T;
     }
   }
-  LlmAttnCur ld = cu;  // load cursor, two half tiles ahead
+  LlmAttnCur ld = cu;  // load cursor, one tile ahead
   int f_ld = lo;
-  int pg = __ldg(page_table + ld.b * max_pages + (ld.ht >> 1));
+  int pg = __ldg(page_table + ld.b * max_pages + ld.kt);
+  // measurement switches (bd_stream_set_tuning mode; scripts/llm_timeline.py): 64 no K/V loads, 128 no tensor work / softmax
+  const bool no_loads = (dbg_mode & 64) != 0, no_math = (dbg_mode & 128) != 0;
+  long long t_wait = 0, t_math = 0;
+  // per-thread constants of the tile copies: chunk ch of rows r0 + kRowStep * k
+  const int cp_r0 = tid / kChunks, cp_ch = tid % kChunks;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t cp_dst0 = static_cast<uint32_t>(cp_r0 * (HD * 2) + ((cp_ch ^ (cp_r0 & 7)) << 4));
+  const int cp_src0 = cp_r0 * HD + cp_ch * 8;
   auto issue = [&](int buf) {
     if (f_ld < hi) {
-      const int hk = ld.h / (Hq / Hkv);
-      const long long off = ((static_cast<long long>(pg) * Hkv + hk) * 64 + (ld.ht & 1) * 32) * HD;
-      const int valid = min(32, ld.Sk - ld.ht * 32);
-      uint8_t* dst = smem + buf * kStage;
-      htile_load_async<HD>(dst, kpool + off, valid, tid);
-      htile_load_async<HD>(dst + kHalf, vpool + off, valid, tid);
-      llm_attn_advance(ld, seq_lens, R, S, Hq);
-      if (++f_ld < hi) pg = __ldg(page_table + ld.b * max_pages + (ld.ht >> 1));  // consumed one half tile later
+      const __nv_bfloat16* src = kpool + (static_cast<long long>(pg) * Hkv + ld.hk) * (64 * HD) + cp_src0;
+      const uint32_t dst = smem_base + buf * kStage + cp_dst0;
+      const int valid = ld.Sk - ld.kt * 64;
+      if (!no_loads) {
+        if (valid >= 64) {
+#pragma unroll
+          for (int k = 0; k < kCopies; ++k) {
+            cp_async16_s(dst + k * (kRowStep * HD * 2), src + k * (kRowStep * HD));
+            cp_async16_s(dst + kTile + k * (kRowStep * HD * 2), src + v_off + k * (kRowStep * HD));
+          }
+        } else {  // the last tile of a sequence: rows past the end are zero-filled
+#pragma unroll
+          for (int k = 0; k < kCopies; ++k) {
+            const bool ok = cp_r0 + k * kRowStep < valid;
+            const __nv_bfloat16* sk = ok ? src + k * (kRowStep * HD) : src - cp_r0 * HD;
+            cp_async16_sz(dst + k * (kRowStep * HD * 2), sk, ok);
+            cp_async16_sz(dst + kTile + k * (kRowStep * HD * 2), sk + v_off, ok);
+          }
+        }
+      }
+      llm_attn_advance(ld, seq_lens, R, S, Hq, gqa);
+      if (++f_ld < hi) pg = __ldg(page_table + ld.b * max_pages + ld.kt);  // consumed one tile later
     }
     cp_async_commit();
   };
   issue(0);
-  issue(1);
+  // per-lane ldmatrix offsets inside a tile (the swizzle phase is the lane's row & 7)
+  uint32_t k_off[HD / 32], v_offs[HD / 16];
+#pragma unroll
+  for (int i = 0; i < HD / 32; ++i) k_off[i] = ltile_off<HD>(lane & 7, 4 * i + (lane >> 3));
+#pragma unroll
+  for (int i = 0; i < HD / 16; ++i) v_offs[i] = ltile_off<HD>((lane & 7) + 8 * ((lane >> 3) & 1), 2 * i + (lane >> 4));
   uint32_t qf[HD / 16][4];
   float o_acc[HD / 8][4];
-  float m_run[2], l_run[2];
+  float m_run[2], l_run[2];  // running maximum of the RAW scores, running sum of exp2((s - m) * scale_log2) per thread
   bool fresh = true;
   const int n_st = hi - lo;
   for (int i = 0; i < n_st; ++i) {
@@ -1139,15 +1224,14 @@ __device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int 
       fresh = false;
       const __nv_bfloat16* qb = q + (static_cast<long long>(cu.b) * S * Hq + cu.h) * HD;
       const int r0 = warp * 16 + g, r1 = r0 + 8;
+      const unsigned int* p0 = reinterpret_cast<const unsigned int*>(qb + static_cast<long long>(r0) * Hq * HD + 2 * t);
+      const unsigned int* p1 = reinterpret_cast<const unsigned int*>(qb + static_cast<long long>(r1) * Hq * HD + 2 * t);
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks) {
-        const int col = 16 * ks + 2 * t;
-        const unsigned int* p0 = reinterpret_cast<const unsigned int*>(qb + static_cast<long long>(r0) * Hq * HD + col);
-        const unsigned int* p1 = reinterpret_cast<const unsigned int*>(qb + static_cast<long long>(r1) * Hq * HD + col);
-        qf[ks][0] = r0 < S ? __ldcg(p0) : 0u;
-        qf[ks][1] = r1 < S ? __ldcg(p1) : 0u;
-        qf[ks][2] = r0 < S ? __ldcg(p0 + 4) : 0u;
-        qf[ks][3] = r1 < S ? __ldcg(p1 + 4) : 0u;
+        qf[ks][0] = r0 < S ? __ldcg(p0 + 8 * ks) : 0u;
+        qf[ks][1] = r1 < S ? __ldcg(p1 + 8 * ks) : 0u;
+        qf[ks][2] = r0 < S ? __ldcg(p0 + 8 * ks + 4) : 0u;
+        qf[ks][3] = r1 < S ? __ldcg(p1 + 8 * ks + 4) : 0u;
       }
 #pragma unroll
       for (int n = 0; n < HD / 8; ++n)
@@ -1156,89 +1240,102 @@ __device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int 
       m_run[0] = m_run[1] = -FLT_MAX;
       l_run[0] = l_run[1] = 0.f;
     }
-    cp_async_wait<1>();  // half tile i landed (i + 1 may still be in flight)
-    epi_bar();           // ... for every thread's share, and every warp is done with half tile i - 1
-    issue((i + 2) % 3);  // refill the buffer half tile i - 1 used
-    const uint8_t* sK = smem + (i % 3) * kStage;
-    const uint8_t* sV = sK + kHalf;
-    const int k0 = cu.ht * 32;
-    float sc[4][4];
+    const long long tw0 = dbg_slot ? clock64() : 0;
+    epi_bar();           // every warp is done with tile i - 1: its buffer can be refilled
+    issue((i + 1) & 1);
+    cp_async_wait<1>();  // tile i landed (tile i + 1 in flight)
+    epi_bar();           // ... for every thread's share
+    const long long tw1 = dbg_slot ? clock64() : 0;
+    t_wait += tw1 - tw0;
+    if (no_math) {
+      llm_attn_advance(cu, seq_lens, R, S, Hq, gqa);
+      continue;
+    }
+    const uint32_t sK = smem_base + (i & 1) * kStage;
+    const uint32_t sV = sK + kTile;
+    float sc[8][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ks += 2) {
+    for (int kq = 0; kq < HD / 32; ++kq) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t bk[4];
-        s_ldmatrix_x4(bk, smem_u32(sK + ltile_off<HD>(8 * j + (lane & 7), 2 * ks + (lane >> 3))));
-        s_mma_16816(sc[j], qf[ks], bk[0], bk[1]);
-        s_mma_16816(sc[j], qf[ks + 1], bk[2], bk[3]);
+      for (int jh = 0; jh < 8; jh += 4) {  // 4 key blocks at a time: 4 independent chains, 2 k-steps each
+        uint32_t bk[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_ldmatrix_x4(bk[j], sK + k_off[kq] + (jh + j) * (8 * HD * 2));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_mma_16816_nv(sc[jh + j], qf[2 * kq], bk[j][0], bk[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_mma_16816_nv(sc[jh + j], qf[2 * kq + 1], bk[j][2], bk[j][3]);
       }
+    }
+    const int k0 = cu.kt * 64;
+    if (k0 + 64 > cu.Sk) {  // the last tile of the sequence: keys past the end do not count
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k0 + 8 * j + 2 * t + (e & 1) >= cu.Sk) sc[j][e] = -FLT_MAX;
     }
     float m_new[2] = {m_run[0], m_run[1]};
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = k0 + 8 * j + 2 * t + (e & 1);
-        const float v = key < cu.Sk ? sc[j][e] * scale_log2 : -FLT_MAX;
-        sc[j][e] = v;
-        m_new[e >> 1] = fmaxf(m_new[e >> 1], v);
-      }
+      for (int e = 0; e < 4; ++e) m_new[e >> 1] = fmaxf(m_new[e >> 1], sc[j][e]);
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
       m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
     }
-    float corr[2], l_add[2] = {0.f, 0.f};
+    if (__any_sync(0xffffffffu, (m_new[0] > m_run[0]) || (m_new[1] > m_run[1]))) {  // a maximum moved: rescale
+      float corr[2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) corr[r] = exp2f(m_run[r] - m_new[r]);
-    uint32_t pa[2][4];
+      for (int r = 0; r < 2; ++r) {
+        corr[r] = ex2_approx((m_run[r] - m_new[r]) * scale_log2);
+        l_run[r] *= corr[r];
+        m_run[r] = m_new[r];
+      }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+      for (int n = 0; n < HD / 8; ++n) {
+        o_acc[n][0] *= corr[0];
+        o_acc[n][1] *= corr[0];
+        o_acc[n][2] *= corr[1];
+        o_acc[n][3] *= corr[1];
+      }
+    }
+    const float ms[2] = {m_run[0] * scale_log2, m_run[1] * scale_log2};
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
       float e[4];
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
-        e[x] = (sc[j][x] == -FLT_MAX) ? 0.f : exp2f(sc[j][x] - m_new[x >> 1]);
-        l_add[x >> 1] += e[x];
+        e[x] = ex2_approx(fmaf(sc[j][x], scale_log2, -ms[x >> 1]));
+        l_run[x >> 1] += e[x];
       }
-      const int kk = j >> 1;
-      if ((j & 1) == 0) {
-        pa[kk][0] = s_pack_bf16(e[0], e[1]);
-        pa[kk][1] = s_pack_bf16(e[2], e[3]);
-      } else {
-        pa[kk][2] = s_pack_bf16(e[0], e[1]);
-        pa[kk][3] = s_pack_bf16(e[2], e[3]);
-      }
+      pa[j >> 1][(j & 1) * 2] = s_pack_bf16(e[0], e[1]);
+      pa[j >> 1][(j & 1) * 2 + 1] = s_pack_bf16(e[2], e[3]);
     }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      l_run[r] = l_run[r] * corr[r] + l_add[r];
-      m_run[r] = m_new[r];
-    }
+    for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-    for (int n = 0; n < HD / 8; ++n) {
-      o_acc[n][0] *= corr[0];
-      o_acc[n][1] *= corr[0];
-      o_acc[n][2] *= corr[1];
-      o_acc[n][3] *= corr[1];
-    }
+      for (int nh = 0; nh < HD / 16; nh += 4) {  // 8 dim blocks at a time
+        uint32_t bv[4][4];
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
+        for (int n = 0; n < 4; ++n) s_ldmatrix_x4_trans(bv[n], sV + v_offs[nh + n] + kk * (16 * HD * 2));
 #pragma unroll
-      for (int n = 0; n < HD / 8; n += 2) {
-        uint32_t bv[4];
-        s_ldmatrix_x4_trans(bv, smem_u32(sV + ltile_off<HD>(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), n + (lane >> 4))));
-        s_mma_16816(o_acc[n], pa[kk], bv[0], bv[1]);
-        s_mma_16816(o_acc[n + 1], pa[kk], bv[2], bv[3]);
+        for (int n = 0; n < 4; ++n) {
+          s_mma_16816_nv(o_acc[2 * (nh + n)], pa[kk], bv[n][0], bv[n][1]);
+          s_mma_16816_nv(o_acc[2 * (nh + n) + 1], pa[kk], bv[n][2], bv[n][3]);
+        }
       }
     }
-    if (cu.ht == cu.T32 - 1 || i == n_st - 1) {  // the block (or this CTA's share of it) ends: store the segment
+    if (cu.kt == cu.T - 1 || i == n_st - 1) {  // the block (or this CTA's share of it) ends: store the segment
       fresh = true;
       const int hb = cu.b * Hq + cu.h;
-      const int seg = c - llm_attn_cta_of(cu.base + cu.h * cu.T32, Ge, P);
+      const int seg = c - llm_attn_cta_of(cu.base + cu.h * cu.T, Ge, P);
       if (seg < 0 || seg >= maxseg) __trap();
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -1252,13 +1349,19 @@ __device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int 
 #pragma unroll
         for (int n = 0; n < HD / 8; ++n)
           *reinterpret_cast<float2*>(o + 8 * n + 2 * t) = make_float2(o_acc[n][2 * r], o_acc[n][2 * r + 1]);
-        if (t == 0) *reinterpret_cast<float2*>(part_ml + row * 2) = make_float2(m_run[r], l);
+        // the combine works in the exp2 domain of bd_attn.cu: maximum of the SCALED scores
+        if (t == 0) *reinterpret_cast<float2*>(part_ml + row * 2) = make_float2(m_run[r] * scale_log2, l);
       }
     }
-    llm_attn_advance(cu, seq_lens, R, S, Hq);
+    llm_attn_advance(cu, seq_lens, R, S, Hq, gqa);
+    if (dbg_slot) t_math += clock64() - tw1;
   }
   cp_async_wait<0>();
   epi_bar();
+  if (dbg_slot && tid == 0) {  // timeline slots 6 / 7 of this op: cycles waiting for K/V, cycles from landed to next wait
+    dbg_slot[6] = static_cast<unsigned long long>(t_wait);
+    dbg_slot[7] = static_cast<unsigned long long>(t_math);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1758,8 +1861,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
             if (op.K == 128) llm_rope_append<128>(op, it, c, G, tid);
             else llm_rope_append<64>(op, it, c, G, tid);
           } else if (op.kind == kOpLlmAttn && c < op.act) {
-            if (op.K == 128) llm_attn_stream<128>(op, it, c, tid, smem_a);
-            else llm_attn_stream<64>(op, it, c, tid, smem_a);
+            unsigned long long* slot =
+                (prog.dbg && q < prog.dbg_ops) ? prog.dbg + (static_cast<long long>(q) * G + c) * 8 : nullptr;
+            if (op.K == 128) llm_attn_stream<128>(op, it, c, tid, smem_a, prog.dbg_mode, slot);
+            else llm_attn_stream<64>(op, it, c, tid, smem_a, prog.dbg_mode, slot);
           }
         } else if (op.kind == kOpAttn) {
           const int units = (prog.M / op.i0) * (op.N / op.K);

@@ -346,6 +346,10 @@ int bd_stream_gemm_filler(const void* A_blocked, const void* W_main, const void*
 int bd_probe_stream(const void* w, long long w_per_cta, int w_chunk, int w_stages, const void* x, int x_bytes,
                     int x_chunk, int x_stages, int n_ctas, bd_stream_t stream);
 
+/* measurement only (scripts/hmma_probe.py): per-warp cycles of `iters` rounds of `chains` independent
+ * mma.sync.m16n8k16 (bf16, fp32 accumulate) with `warps` warps per CTA -> out_cycles[n_ctas * warps]. */
+int bd_probe_hmma(int warps, int chains, int iters, int n_ctas, long long* out_cycles, float* sink, bd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

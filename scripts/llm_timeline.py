@@ -56,28 +56,48 @@ print(f"one AR block, {L} layers, context {ctx}: {ms * 1e3:.1f} us = {ms * 1e3 /
 G = ops.stream_num_ctas()
 names_body = ["rope", "attn", "combine", "wo", "row_wo", "gate_up", "down", "row_down", "qkv_next"]
 nops = 2 + 9 * L + 1
-dbg = torch.zeros(nops * G * 8, dtype=torch.int64, device=dev)
-lib.bd_stream_set_debug(C.c_void_p(dbg.data_ptr()), nops)
-block()
-torch.cuda.synchronize()
-lib.bd_stream_set_debug(None, 0)
-d = dbg.view(nops, G, 8).cpu().double() / 1e3
 names = ["rms0", "qkv0"] + names_body * L + ["final"]
-t_prev = None
-tot = {}
-for q in range(nops):
-    v = d[q, :, 5]
-    v = v[v > 0]
-    if v.numel() == 0:
-        continue
-    done = v.max().item()
-    if t_prev is None:
-        t_prev = d[q, :, 4][d[q, :, 4] > 0].min().item()
-    dur = done - t_prev
-    layer = (q - 2) // 9
-    if 2 <= q < nops - 1 and layer == L // 2:
-        print(f"  layer {layer} {names[q]:10s} {dur:7.1f} us   (arrive spread {done - v.median().item():.1f})")
-    if 2 <= q < nops - 1 and 1 <= layer < L - 1:
-        tot[names[q]] = tot.get(names[q], 0.0) + dur / (L - 2)
-    t_prev = done
-print("mean per op over the inner layers (us):", {k: round(v, 1) for k, v in tot.items()}, "sum", round(sum(tot.values()), 1))
+
+
+def timeline(label, verbose):
+    dbg = torch.zeros(nops * G * 8, dtype=torch.int64, device=dev)
+    lib.bd_stream_set_debug(C.c_void_p(dbg.data_ptr()), nops)
+    block()
+    torch.cuda.synchronize()
+    lib.bd_stream_set_debug(None, 0)
+    d = dbg.view(nops, G, 8).cpu().double()
+    t_prev = None
+    tot = {}
+    for q in range(nops):
+        v = d[q, :, 5] / 1e3
+        v = v[v > 0]
+        if v.numel() == 0:
+            continue
+        done = v.max().item()
+        if t_prev is None:
+            t4 = d[q, :, 4] / 1e3
+            t_prev = t4[t4 > 0].min().item()
+        dur = done - t_prev
+        layer = (q - 2) // 9
+        if verbose and 2 <= q < nops - 1 and layer == L // 2:
+            print(f"  layer {layer} {names[q]:10s} {dur:7.1f} us   (arrive spread {done - v.median().item():.1f})")
+        if 2 <= q < nops - 1 and 1 <= layer < L - 1:
+            tot[names[q]] = tot.get(names[q], 0.0) + dur / (L - 2)
+        t_prev = done
+    qa = 2 + 9 * (L // 2) + 1  # the attention op of the middle layer: slots 6 / 7 = cycles waiting for K/V, cycles of work
+    w, m = d[qa, :, 6], d[qa, :, 7]
+    print(f"{label}: per op (us) {({k: round(v, 1) for k, v in tot.items()})} sum {sum(tot.values()):.1f}; attention of layer "
+          f"{L // 2}: median wait {w.median().item() / 1e3:.1f} kcycles, work {m.median().item() / 1e3:.1f} kcycles per CTA")
+
+
+timeline("default", True)
+for label, mode, poll, pf in (("no K/V loads (mode 64)", 64, 32, 0), ("no tensor work (mode 128)", 128, 32, 0),
+                              ("neither (mode 192)", 192, 32, 0), ("poll 500 ns", 0, 500, 0), ("poll 2000 ns", 0, 2000, 0),
+                              ("L2 prefetch 8 steps", 0, 32, 8)):
+    lib.bd_stream_set_tuning(5, 2, mode)
+    lib.bd_stream_set_poll_ns(poll)
+    lib.bd_stream_set_prefetch(pf)
+    timeline(label, False)
+lib.bd_stream_set_tuning(5, 2, 0)
+lib.bd_stream_set_poll_ns(32)
+lib.bd_stream_set_prefetch(0)
