@@ -914,6 +914,27 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
   epi_bar();  // tiles (aliasing the A ring) dead
 }
 
+// The op descriptor is a copy of a kernel parameter: left alone, the compiler re-reads its fields from the constant bank
+// with a run-time index wherever they are used (an IMAD + LDC chain in front of every use in the tile loop). pin() makes
+// the value opaque, so it stays in a register.
+__device__ __forceinline__ int pin(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ long long pin(long long v) {
+  asm volatile("" : "+l"(v));
+  return v;
+}
+__device__ __forceinline__ float pin(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T* pin(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Qwen3 decoder ops inside the engine (one persistent launch per AR block: csrc/bd_llm.cu::llm_stream_all)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -922,39 +943,56 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
 template <int HD>
 __device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int c, int G, int tid) {
   constexpr int VPT = HD / 32;
-  const int S = op.i0, Hq = op.i1, Hkv = op.i2, heads = Hq + 2 * Hkv, max_pages = op.N;
+  const int S = pin(op.i0), Hq = pin(op.i1), Hkv = pin(op.i2), heads = pin(Hq + 2 * Hkv), max_pages = pin(op.N);
   const int M = op.i0 * op.sub;  // sub = number of sequences
   const int warp = tid >> 5, lane = tid & 31;
-  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(op.p0);
+  const __nv_bfloat16* qkv = pin(reinterpret_cast<const __nv_bfloat16*>(op.p0));
   const __nv_bfloat16* qn_w = reinterpret_cast<const __nv_bfloat16*>(op.p1);
   const __nv_bfloat16* kn_w = reinterpret_cast<const __nv_bfloat16*>(op.p2);
-  const float* rope_cos = reinterpret_cast<const float*>(op.p3);
-  const float* rope_sin = reinterpret_cast<const float*>(op.p4);
+  const float* rope_cos = pin(reinterpret_cast<const float*>(op.p3));
+  const float* rope_sin = pin(reinterpret_cast<const float*>(op.p4));
   const int* seq_lens = reinterpret_cast<const int*>(op.p5);
-  const int* page_table = reinterpret_cast<const int*>(op.p6);
-  __nv_bfloat16* q_out = reinterpret_cast<__nv_bfloat16*>(op.o0);
-  __nv_bfloat16* kpool = reinterpret_cast<__nv_bfloat16*>(op.o1) + static_cast<long long>(it) * op.l0;
+  const int* page_table = pin(reinterpret_cast<const int*>(op.p6));
+  __nv_bfloat16* q_out = pin(reinterpret_cast<__nv_bfloat16*>(op.o0));
+  __nv_bfloat16* kpool = pin(reinterpret_cast<__nv_bfloat16*>(op.o1) + static_cast<long long>(it) * op.l0);
   __nv_bfloat16* vpool = kpool + op.l1;
-  const long long tasks = static_cast<long long>(M) * heads;
-  const long long stride = static_cast<long long>(G) * 4;
+  const float eps = pin(op.f0);
+  float qw[VPT], kw[VPT];  // the lane's slice of the q / k norm weights
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    qw[j] = __bfloat162float(qn_w[lane * VPT + j]);
+    kw[j] = __bfloat162float(kn_w[lane * VPT + j]);
+  }
+  const int tasks = M * heads;  // (token, head) pairs; 32-bit index arithmetic (a 64-bit division is a ~150-instruction call)
+  const int stride = G * 4;
+  const int d_m = stride / heads, d_h = stride % heads;  // task + stride = (token + d_m, head + d_h) with one carry
   constexpr int U = 6;  // tasks in flight per warp (12 tasks per warp at the 14B shape): two rounds of one L2 round trip
   // the sequence lengths once per warp (lane b holds sequence b's; more than 32 sequences: read per task)
   const int R = op.sub;
   const int len_lane = (lane < R) ? __ldcg(seq_lens + lane) : 0;
-  for (long long gw0 = static_cast<long long>(c) * 4 + warp; gw0 < tasks; gw0 += stride * U) {
+  for (int gw0 = c * 4 + warp; gw0 < tasks; gw0 += stride * U) {
     float x[U][VPT], cs[U][VPT], sn[U][VPT];
-    int pos[U], page[U];
+    int pos[U], page[U], tm[U], th[U];
     bool live[U];
+    int m_u = gw0 / heads, h_u = gw0 % heads;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long gw = gw0 + u * stride;
+      const int gw = gw0 + u * stride;
       live[u] = gw < tasks;
       pos[u] = 0;
       page[u] = 0;
+      tm[u] = m_u;
+      th[u] = h_u;
+      m_u += d_m;
+      h_u += d_h;
+      if (h_u >= heads) {
+        h_u -= heads;
+        ++m_u;
+      }
 #pragma unroll
       for (int j = 0; j < VPT; ++j) x[u][j] = cs[u][j] = sn[u][j] = 0.f;
       if (!live[u]) continue;
-      const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
+      const int m = tm[u], hh = th[u];
       const int b = m / S, sidx = m % S;
       pos[u] = (R <= 32 ? __shfl_sync(0xffffffffu, len_lane, b) : __ldcg(seq_lens + b)) + sidx;
       if (pos[u] < 0 || pos[u] >= max_pages * 64) __trap();  // outside the KV cache (the host checks the bound too)
@@ -988,8 +1026,7 @@ __device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!live[u]) continue;   // warp-uniform
-      const long long gw = gw0 + u * stride;
-      const int m = static_cast<int>(gw / heads), hh = static_cast<int>(gw % heads);
+      const int m = tm[u], hh = th[u];
       const bool is_q = hh < Hq, is_k = !is_q && hh < Hq + Hkv;
       __nv_bfloat16* dst;
       if (is_q) {
@@ -1008,11 +1045,10 @@ __device__ __forceinline__ void llm_rope_append(const StreamOp& op, int it, int 
         for (int j = 0; j < VPT; ++j) ss += x[u][j] * x[u][j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float rstd = rsqrtf(ss / static_cast<float>(HD) + op.f0);
-        const __nv_bfloat16* nw = is_q ? qn_w : kn_w;
+        const float rstd = rsqrtf(ss / static_cast<float>(HD) + eps);
         float xn[VPT];
 #pragma unroll
-        for (int j = 0; j < VPT; ++j) xn[j] = bf16_round(__bfloat162float(nw[lane * VPT + j]) * bf16_round(x[u][j] * rstd));
+        for (int j = 0; j < VPT; ++j) xn[j] = bf16_round((is_q ? qw[j] : kw[j]) * bf16_round(x[u][j] * rstd));
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
           const float other = __shfl_xor_sync(0xffffffffu, xn[j], 16);
@@ -1107,27 +1143,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// The op descriptor is a copy of a kernel parameter: left alone, the compiler re-reads its fields from the constant bank
-// with a run-time index wherever they are used (an IMAD + LDC chain in front of every use in the tile loop). pin() makes
-// the value opaque, so it stays in a register.
-__device__ __forceinline__ int pin(int v) {
-  asm volatile("" : "+r"(v));
-  return v;
-}
-__device__ __forceinline__ long long pin(long long v) {
-  asm volatile("" : "+l"(v));
-  return v;
-}
-__device__ __forceinline__ float pin(float v) {
-  asm volatile("" : "+f"(v));
-  return v;
-}
-template <typename T>
-__device__ __forceinline__ T* pin(T* p) {
-  asm volatile("" : "+l"(p));
-  return p;
 }
 
 template <int HD>
