@@ -1268,82 +1268,85 @@ __device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int 
     }
     const uint32_t sK = smem_base + (i & 1) * kStage;
     const uint32_t sV = sK + kTile;
-    float sc[8][4];
+    const int k0 = cu.kt * 64;
+    // two halves of 32 keys, each QK^T -> online softmax -> P V: half the score / P registers of a whole-tile pass, which
+    // is what lets the compiler keep loads of the next fragments in flight (255 registers: 64 of O, 32 of Q)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int half = 0; half < 2; ++half) {
+      float sc[4][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int kq = 0; kq < HD / 32; ++kq) {
+        for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
 #pragma unroll
-      for (int jh = 0; jh < 8; jh += 4) {  // 4 key blocks at a time: 4 independent chains, 2 k-steps each
+      for (int kq = 0; kq < HD / 32; ++kq) {  // 4 key blocks = 4 independent chains, 2 k-steps each
         uint32_t bk[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s_ldmatrix_x4(bk[j], sK + k_off[kq] + (jh + j) * (8 * HD * 2));
+        for (int j = 0; j < 4; ++j) s_ldmatrix_x4(bk[j], sK + k_off[kq] + (4 * half + j) * (8 * HD * 2));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s_mma_16816_nv(sc[jh + j], qf[2 * kq], bk[j][0], bk[j][1]);
+        for (int j = 0; j < 4; ++j) s_mma_16816_nv(sc[j], qf[2 * kq], bk[j][0], bk[j][1]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s_mma_16816_nv(sc[jh + j], qf[2 * kq + 1], bk[j][2], bk[j][3]);
+        for (int j = 0; j < 4; ++j) s_mma_16816_nv(sc[j], qf[2 * kq + 1], bk[j][2], bk[j][3]);
       }
-    }
-    const int k0 = cu.kt * 64;
-    if (k0 + 64 > cu.Sk) {  // the last tile of the sequence: keys past the end do not count
+      if (k0 + 32 * half + 32 > cu.Sk) {  // the last tile of the sequence: keys past the end do not count
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (k0 + 8 * j + 2 * t + (e & 1) >= cu.Sk) sc[j][e] = -FLT_MAX;
-    }
-    float m_new[2] = {m_run[0], m_run[1]};
+          for (int e = 0; e < 4; ++e)
+            if (k0 + 32 * half + 8 * j + 2 * t + (e & 1) >= cu.Sk) sc[j][e] = -FLT_MAX;
+      }
+      float m_new[2] = {m_run[0], m_run[1]};
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) m_new[e >> 1] = fmaxf(m_new[e >> 1], sc[j][e]);
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
-      m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
-    }
-    if (__any_sync(0xffffffffu, (m_new[0] > m_run[0]) || (m_new[1] > m_run[1]))) {  // a maximum moved: rescale
-      float corr[2];
+        for (int e = 0; e < 4; ++e) m_new[e >> 1] = fmaxf(m_new[e >> 1], sc[j][e]);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        corr[r] = ex2_approx((m_run[r] - m_new[r]) * scale_log2);
-        l_run[r] *= corr[r];
-        m_run[r] = m_new[r];
+        m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
+        m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
+      }
+      if (__any_sync(0xffffffffu, (m_new[0] > m_run[0]) || (m_new[1] > m_run[1]))) {  // a maximum moved: rescale
+        float corr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          corr[r] = ex2_approx((m_run[r] - m_new[r]) * scale_log2);
+          l_run[r] *= corr[r];
+          m_run[r] = m_new[r];
+        }
+#pragma unroll
+        for (int n = 0; n < HD / 8; ++n) {
+          o_acc[n][0] *= corr[0];
+          o_acc[n][1] *= corr[0];
+          o_acc[n][2] *= corr[1];
+          o_acc[n][3] *= corr[1];
+        }
+      }
+      const float ms[2] = {m_run[0] * scale_log2, m_run[1] * scale_log2};
+      uint32_t pa[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float e[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          e[x] = ex2_approx(fmaf(sc[j][x], scale_log2, -ms[x >> 1]));
+          l_run[x >> 1] += e[x];
+        }
+        pa[j >> 1][(j & 1) * 2] = s_pack_bf16(e[0], e[1]);
+        pa[j >> 1][(j & 1) * 2 + 1] = s_pack_bf16(e[2], e[3]);
       }
 #pragma unroll
-      for (int n = 0; n < HD / 8; ++n) {
-        o_acc[n][0] *= corr[0];
-        o_acc[n][1] *= corr[0];
-        o_acc[n][2] *= corr[1];
-        o_acc[n][3] *= corr[1];
-      }
-    }
-    const float ms[2] = {m_run[0] * scale_log2, m_run[1] * scale_log2};
-    uint32_t pa[4][4];
+      for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float e[4];
+        for (int nh = 0; nh < HD / 16; nh += 4) {  // 8 dim blocks at a time
+          uint32_t bv[4][4];
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        e[x] = ex2_approx(fmaf(sc[j][x], scale_log2, -ms[x >> 1]));
-        l_run[x >> 1] += e[x];
-      }
-      pa[j >> 1][(j & 1) * 2] = s_pack_bf16(e[0], e[1]);
-      pa[j >> 1][(j & 1) * 2 + 1] = s_pack_bf16(e[2], e[3]);
-    }
+          for (int n = 0; n < 4; ++n)
+            s_ldmatrix_x4_trans(bv[n], sV + v_offs[nh + n] + (2 * half + kk) * (16 * HD * 2));
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int nh = 0; nh < HD / 16; nh += 4) {  // 8 dim blocks at a time
-        uint32_t bv[4][4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) s_ldmatrix_x4_trans(bv[n], sV + v_offs[nh + n] + kk * (16 * HD * 2));
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          s_mma_16816_nv(o_acc[2 * (nh + n)], pa[kk], bv[n][0], bv[n][1]);
-          s_mma_16816_nv(o_acc[2 * (nh + n) + 1], pa[kk], bv[n][2], bv[n][3]);
+          for (int n = 0; n < 4; ++n) {
+            s_mma_16816_nv(o_acc[2 * (nh + n)], pa[kk], bv[n][0], bv[n][1]);
+            s_mma_16816_nv(o_acc[2 * (nh + n) + 1], pa[kk], bv[n][2], bv[n][3]);
+          }
         }
       }
     }
