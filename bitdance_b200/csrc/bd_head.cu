@@ -422,8 +422,8 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
                               size_t workspace_bytes, cudaStream_t st) {
   const int R = B * cfg_mult, M = R * pn, nx = B * pn;
   const int D = w.D, C = w.C, G = w.stream_ctas;
-  BD_REQUIRE(M <= 128 && S + 1 <= kStreamMaxIter && S + 1 <= 128 && G > 0 && G == num_sms());
-  BD_REQUIRE(G >= M && G >= S + 1);  // row ops: token row r (timestep row r) is handled by CTA r
+  BD_REQUIRE(M <= 128 && S + 1 <= kStreamMaxIter && S + 1 <= 128 && G > 0 && G <= num_sms());
+  // row ops: token row r (timestep row r) is handled by CTA r mod G (G < 128: several engines side by side)
   BD_REQUIRE((D % 64) == 0 && (w.Dz % 8) == 0 && C <= 64 && (w.hidden % 8) == 0 && D <= 6144);
   const int n_mod = w.n_ada * 6 * D + 2 * D;
   const HeadStreamWs L = head_stream_ws_layout(w, S);

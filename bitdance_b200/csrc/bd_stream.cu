@@ -1873,7 +1873,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         const bool scratch = op_uses_scratch(prog, op, c);
         if (scratch) mbar_wait(scr_free, scr_uses & 1u);  // the A ring is ours (see op_uses_scratch)
         if (op.kind == kOpRow) {
+          // one token row (or schedule row) per CTA; a grid smaller than the 128-row tile (several engines side by side,
+          // each on its share of the SMs: the ImageNet sampler) takes its rows round-robin
           row_op<FAM>(prog, op, it, c, tid, red, smem_a);
+          for (int r = c + G; r < 128; r += G) {
+            epi_bar();  // the reduction scratch of the previous row is dead
+            row_op<FAM>(prog, op, it, r, tid, red, smem_a);
+          }
         } else if constexpr (FAM == kStreamFamLlm) {
           if (op.kind == kOpLlmRope) {
             if (op.K == 128) llm_rope_append<128>(op, it, c, G, tid);
@@ -1886,9 +1892,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           }
         } else if (op.kind == kOpAttn) {
           const int units = (prog.M / op.i0) * (op.N / op.K);
-          if (c < units) {
-            if (op.K == 128) attn_unit<128>(op, c, tid, smem_a, aux_bar, aux_uses & 1u);
-            else attn_unit<64>(op, c, tid, smem_a, aux_bar, aux_uses & 1u);
+          for (int u = c; u < units; u += G) {
+            if (op.K == 128) attn_unit<128>(op, u, tid, smem_a, aux_bar, aux_uses & 1u);
+            else attn_unit<64>(op, u, tid, smem_a, aux_bar, aux_uses & 1u);
             ++aux_uses;
           }
         }

@@ -99,15 +99,21 @@ class HeadRunner:
     """Prepacked weights + workspace for one DiffHead on one device."""
 
     def __init__(self, state_dict: dict, *, ch_target, ch_cond, ch_latent, depth_latent, depth_adanln, use_swiglu,
-                 head_dim=128, out_sigmoid=True, time_shift=1.0, device="cuda", prefix="net.", stream=True, tiled=True):
+                 head_dim=128, out_sigmoid=True, time_shift=1.0, device="cuda", prefix="net.", stream=True, tiled=True,
+                 stream_ctas: int | None = None):
         """stream: also pack the weights stream-major for the persistent kernel (used whenever B*cfg_mult*pn <= 128);
-        tiled: keep the tile-major copy for the multi-kernel path (larger batches)."""
+        tiled: keep the tile-major copy for the multi-kernel path (larger batches);
+        stream_ctas: grid of one persistent engine (default: every SM). A small model whose weights live in L2 is better
+        served by several engines side by side, each on its share of the SMs and its own 128-row tile (``sample(...,
+        slot=i)`` on CUDA stream i): the ImageNet class-conditional sampler."""
         assert depth_latent <= MAX_BLOCKS
         self.device = torch.device(device)
         self.cfg = dict(C=ch_target, Dz=ch_cond, D=ch_latent, n_blocks=depth_latent, n_ada=depth_adanln)
         self.time_shift = time_shift
         self.hidden = int(ch_latent * 1.5)
         self._keep = []  # prepacked tensors (owned here; C side sees raw pointers)
+        self.stream_ctas = int(stream_ctas) if stream_ctas else ops.stream_num_ctas()
+        assert 1 <= self.stream_ctas <= ops.stream_num_ctas()
         dev = self.device
         D, hidden = ch_latent, self.hidden
         # the persistent kernel needs 16-row units everywhere and one 64-column k-block for the latent bits
@@ -133,7 +139,7 @@ class HeadRunner:
             keep.append(t)
             return t.data_ptr()
 
-        n_ctas = ops.stream_num_ctas() if kind == "stream" else 0
+        n_ctas = self.stream_ctas if kind == "stream" else 0
 
         def lin(wt, bias, *, ksplit=1, swiglu=False):
             """-> (weight ptr, bias ptr) in the layout of `kind`; the row-major copy is dropped"""
@@ -184,11 +190,11 @@ class HeadRunner:
             self._sched[S] = sampler_schedule(S, self.time_shift, device=self.device)
         return self._sched[S]
 
-    def _workspace(self, w, B, pn, mult, S):
+    def _workspace(self, w, B, pn, mult, S, slot=0):
         lib = _lib.load()
         lib.bd_head_workspace_bytes.restype = C.c_size_t
         need = lib.bd_head_workspace_bytes(C.byref(w), B, pn, mult, S)
-        key = int(w.w_tiled)
+        key = (int(w.w_tiled), int(slot))
         if key not in self._ws or self._ws[key].numel() < need:
             self._ws[key] = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws[key]
@@ -215,9 +221,10 @@ class HeadRunner:
         return noise
 
     def sample(self, z: torch.Tensor, cfg: float, num_sampling_steps: int, noise: torch.Tensor | None = None,
-               trace: bool = False, pdl: bool = True, path: str | None = None):
+               trace: bool = False, pdl: bool = True, path: str | None = None, slot: int = 0):
         """z: [R, pn, Dz] fp32 (cond rows then uncond rows when cfg > 1). Returns x [B, pn, C] fp32 (+ trace).
-        path: None = automatic, "stream" = the persistent kernel, "tiled" = the multi-kernel path."""
+        path: None = automatic, "stream" = the persistent kernel, "tiled" = the multi-kernel path.
+        slot: which private workspace to use (calls in flight at the same time on different CUDA streams need their own)."""
         lib = _lib.load()
         assert z.is_cuda and z.dim() == 3
         mult = 2 if cfg > 1.0 else 1
@@ -233,7 +240,7 @@ class HeadRunner:
         out = torch.empty((B, pn, Cc), dtype=torch.float32, device=self.device)
         tr = torch.empty((S + 1, R * pn, Cc), dtype=torch.float32, device=self.device) if trace else None
         w = self.weights_for(R * pn, S, path)
-        ws = self._workspace(w, B, pn, mult, S)
+        ws = self._workspace(w, B, pn, mult, S, slot)
         sched = self.schedule(S)
         st = lib.bd_head_sample(C.byref(w), ptr(zc), ptr(noise), C.c_void_p(sched.data_ptr()), B, pn, mult,
                                 C.c_float(cfg), S, ptr(out), ptr(tr), ptr(ws), C.c_size_t(ws.numel()),

@@ -26,6 +26,8 @@ from __future__ import annotations
 import ctypes as C
 import math
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -100,11 +102,16 @@ class ImageNetEngine:
 
     MAX_SEQ_PER_PASS = 256   # bd_llm_forward: device-side sequence lengths for up to 256 sequences per call
 
-    def __init__(self, state_dict: dict, cfg: dict, ae=None, device="cuda", head_rows_per_call: int = 8192):
+    def __init__(self, state_dict: dict, cfg: dict, ae=None, device="cuda", head_rows_per_call: int = 8192,
+                 head_engines: int | None = None):
         """state_dict: the reference ``BitDance`` keys (``layers.N.attention.wqkv.weight`` ...), ``vae.*`` ignored;
         cfg: dim, n_layer, n_head, diff_layers, diff_dim, diff_adanln_layers, latent_dim, down_size, patch_size, resolution,
         cls_token_num, num_classes, parallel_num, parallel_mode, time_shift; ae: an ``AERunner`` (or None: sample() then
-        returns the latent grid)."""
+        returns the latent grid).
+        head_engines: how many persistent head engines run side by side, each on num_SMs / head_engines SMs and one 128-row
+        tile of the batch (0 / 1: the multi-kernel path for the whole batch). Default 16 (BD_IMAGENET_HEAD_ENGINES): the
+        sampler's weights (80 MB for BitDance-B) live in L2, the work per Linear is a few microseconds, and the multi-kernel
+        path spends its time between kernels."""
         self.cfg, self.device, self.ae = dict(cfg), torch.device(device), ae
         dev = self.device
         dim, L, H = cfg["dim"], cfg["n_layer"], cfg["n_head"]
@@ -137,9 +144,18 @@ class ImageNetEngine:
         del hf
         lat = cfg["latent_dim"] * cfg["patch_size"] ** 2
         head_sd = {"net." + k[len("head.net."):]: v for k, v in sd.items() if k.startswith("head.net.")}
+        if head_engines is None:
+            head_engines = int(os.environ.get("BD_IMAGENET_HEAD_ENGINES", "16"))
+        n_sm = ops.stream_num_ctas()
+        self.head_engines = max(0, min(int(head_engines), n_sm))
+        eng_ctas = n_sm // self.head_engines if self.head_engines > 1 else None
         self.head = HeadRunner(head_sd, ch_target=lat, ch_cond=dim, ch_latent=cfg["diff_dim"], depth_latent=cfg["diff_layers"],
                                depth_adanln=cfg["diff_adanln_layers"], use_swiglu=True, head_dim=64, out_sigmoid=False,
-                               time_shift=cfg.get("time_shift", 1.0), device=dev, tiled=True)
+                               time_shift=cfg.get("time_shift", 1.0), device=dev, tiled=True,
+                               stream=self.head_engines > 1, stream_ctas=eng_ctas)
+        if self.head.w_stream is None:
+            self.head_engines = 0
+        self._side = [torch.cuda.Stream(device=dev) for _ in range(self.head_engines if self.head_engines > 1 else 0)]
         self.lat = lat
         bf = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
         ph = int(dim * 1.5)
@@ -184,7 +200,29 @@ class ImageNetEngine:
         guided = cfg_iter > 1.0
         R = z.shape[0]
         n = R // 2 if guided else R
-        per = max(1, self.head_rows_per_call // (self.pn * (2 if guided else 1)))
+        rows_per_seq = self.pn * (2 if guided else 1)
+        if self._side and rows_per_seq <= 128 and S + 1 <= 104:
+            # persistent engines side by side: 128-row tiles of the batch, tile i on CUDA stream / workspace i mod engines
+            per = 128 // rows_per_seq
+            cur = torch.cuda.current_stream(self.device)
+            outs, used = [], set()
+            for i, b0 in enumerate(range(0, n, per)):
+                b1 = min(n, b0 + per)
+                k = i % len(self._side)
+                st = self._side[k]
+                if k not in used:
+                    st.wait_stream(cur)
+                    used.add(k)
+                with torch.cuda.stream(st):   # (z and noise were complete before the first wait_stream above)
+                    nz = None if noise is None else noise[:, b0:b1].contiguous()
+                    zc = torch.cat([z[b0:b1], z[n + b0:n + b1]], dim=0) if guided else z[b0:b1]
+                    o = self.head.sample(zc.contiguous(), cfg_iter if guided else 1.0, S, noise=nz, path="stream", slot=k)
+                o.record_stream(cur)
+                outs.append(o)
+            for k in used:
+                cur.wait_stream(self._side[k])
+            return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        per = max(1, self.head_rows_per_call // rows_per_seq)
         outs = []
         for b0 in range(0, n, per):
             b1 = min(n, b0 + per)

@@ -27,6 +27,8 @@ for step in "$@"; do
     ae)       timeout 900 python scripts/ae_bench.py > gpurun_out/${TAG}_ae_bench.txt 2>&1 ;;
     bench)    timeout 1500 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
     benchref) timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err ;;
+    profile)  TAG=${TAG} bash scripts/gpu_profile.sh > gpurun_out/${TAG}_profile_steps.log 2>&1 ;;
+    bench2)   timeout 1500 python bench.py --steps 2 --warmup 3 --llm-stream 0 > gpurun_out/${TAG}_bench_chained.json 2> gpurun_out/${TAG}_bench_chained.err ;;
     smoke)    timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1 ;;
     *) echo "unknown step $step" ;;
   esac

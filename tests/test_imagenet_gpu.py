@@ -10,11 +10,11 @@ CFG = dict(dim=128, n_layer=2, n_head=2, diff_layers=2, diff_dim=128, diff_adanl
            patch_size=1, resolution=64, cls_token_num=4, num_classes=10, parallel_num=4, parallel_mode="patch", time_shift=1.0)
 
 
-def make(cfg, seed=4):
+def make(cfg, seed=4, head_engines=None):
     from bitdance_b200.imagenet import ImageNetEngine, imagenet_spec
     from bitdance_b200.synth import synth_state_dict
     sd = synth_state_dict(imagenet_spec(cfg), seed=seed, std=0.08)
-    return sd, ImageNetEngine(sd, cfg, ae=None)
+    return sd, ImageNetEngine(sd, cfg, ae=None, head_engines=head_engines)
 
 
 def draw_noise(cfg, n_cls, S, cfg_scale, seed=1):
@@ -30,13 +30,18 @@ def draw_noise(cfg, n_cls, S, cfg_scale, seed=1):
     return out
 
 
-@pytest.mark.parametrize("cfg_scale,cls_num,pn", [(3.0, 4, 4), (1.0, 1, 16), (2.5, 9, 16)])
-def test_imagenet_sample_vs_oracle(cfg_scale, cls_num, pn):
+# head_engines: None = the default (16 persistent head engines side by side, 9 SMs and one 128-row tile each), 0 = the
+# multi-kernel path; 11 sequences x 16 tokens x 2 CFG groups = 3 tiles in flight at once, the last one ragged
+@pytest.mark.parametrize("cfg_scale,cls_num,pn,head_engines,n_img",
+                         [(3.0, 4, 4, None, 3), (1.0, 1, 16, None, 3), (2.5, 9, 16, None, 3), (2.5, 9, 16, 0, 3),
+                          (3.0, 4, 16, None, 11)])
+def test_imagenet_sample_vs_oracle(cfg_scale, cls_num, pn, head_engines, n_img):
     from oracle import imagenet as oi
     cfg = dict(CFG, cls_token_num=cls_num, parallel_num=pn)
-    sd, eng = make(cfg)
+    sd, eng = make(cfg, head_engines=head_engines)
+    assert (len(eng._side) > 1) == (head_engines is None)
     S = 4
-    class_ids = torch.tensor([3, 7, 1])
+    class_ids = torch.tensor([3, 7, 1, 0, 9, 2, 5, 4, 8, 6, 3][:n_img])
     noise = draw_noise(cfg, len(class_ids), S, cfg_scale)
     tokens, packed = eng.sample_tokens(class_ids, S, cfg_scale, noise=[n.cuda() for n in noise])
     torch.cuda.synchronize()
@@ -46,7 +51,8 @@ def test_imagenet_sample_vs_oracle(cfg_scale, cls_num, pn):
     t = tokens.cpu()
     a0 = (t[:, :pn] == tok_ref[:, :pn]).float().mean().item()
     a_all = (t == tok_ref).float().mean().item()
-    print(f"ImageNet sample cfg={cfg_scale} cls={cls_num} pn={pn}: first-block token agreement {a0:.4f}, all blocks {a_all:.4f}")
+    print(f"ImageNet sample cfg={cfg_scale} cls={cls_num} pn={pn} engines={len(eng._side)} images={n_img}: "
+          f"first-block token agreement {a0:.4f}, all blocks {a_all:.4f}")
     # free-running agreement decays with the AR position for a random-init (chaotic) model; the decoder is checked
     # teacher-forced at every position below, and the same figure against the REAL reference is the last test of this file
     assert a0 > 0.95 and a_all > 0.65
