@@ -26,7 +26,7 @@ MODEL = "BitDance-14B-64x"
 METRIC = "1024px images/sec (14B-64x)"
 P_LLM, P_HEAD, P_COND, P_PROJ = 13.2125e9, 1.7585e9, 26.2e6, 26.4e6
 KV_BYTES_PER_TOKEN = 163840
-DEFAULT_LLM_STREAM = False   # set from the round's A/B (profiles/): one persistent launch per Qwen3 AR block
+DEFAULT_LLM_STREAM = True    # one persistent launch per Qwen3 AR block (on par with the chained kernels: profiles/r02_bench_*)
 
 
 def algorithmic_bytes_per_ar_step(R: int, S: int, avg_ctx: float) -> float:

@@ -370,7 +370,8 @@ static int llm_stream_all(const bd_llm_weights_t& w, void* hidden, int R, int S,
   // kLlmMaxSplits the workspace is sized for.
   const int att_ctas = std::min(G, (kLlmMaxSplits - 3) * w.Hq);
   const int splits = att_ctas / w.Hq + 3;
-  (void)sk_bound;
+  // the kernel's work-list arithmetic is 32-bit: (items) x (CTAs) must fit
+  BD_REQUIRE(static_cast<long long>(R) * w.Hq * ((sk_bound + 63) / 64) * att_ctas < (1ll << 31));
   float* part_o = reinterpret_cast<float*>(base + L.attn);
   float* part_ml = part_o + static_cast<size_t>(splits) * R * w.Hq * S * hd;
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(base + L.qkv);

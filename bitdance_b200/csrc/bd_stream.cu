@@ -107,8 +107,9 @@ __device__ __forceinline__ void gemm_epi_chunk(const StreamOp& op, int M, int m,
 // ---------------------------------------------------------------------------------------------------------------------
 // row ops: executed by the 128 epilogue threads of CTA r for token row r
 // split-KV attention of an AR block (llm_attn_stream below): the CTA whose range [c P / Ge, (c + 1) P / Ge) holds item f
-__device__ __forceinline__ int llm_attn_cta_of(long long f, int Ge, int P) {
-  return static_cast<int>(((f + 1) * Ge - 1) / P);  // the CTA whose range [c P / Ge, (c + 1) P / Ge) holds f
+__device__ __forceinline__ int llm_attn_cta_of(int f, int Ge, int P) {
+  // 32-bit: the host guarantees P * Ge < 2^31 (bd_llm.cu); a 64-bit division is a ~150-instruction subroutine
+  return static_cast<int>((static_cast<unsigned>(f + 1) * static_cast<unsigned>(Ge) - 1u) / static_cast<unsigned>(P));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -670,7 +671,7 @@ __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp
       const int vph = HD / 8;
       for (int v = tid; v < Hq * vph; v += 128) {
         const int h = v / vph, d0 = (v % vph) * 8;
-        const long long f0 = base + h * Tb;
+        const int f0 = base + h * Tb;
         const int nseg = llm_attn_cta_of(f0 + Tb - 1, Ge, P) - llm_attn_cta_of(f0, Ge, P) + 1;
         const long long row0 = (static_cast<long long>(b) * Hq + h) * maxseg * S + sq;  // + seg * S
         constexpr int kMaxS = 16;
@@ -1169,8 +1170,8 @@ __device__ __forceinline__ void llm_attn_stream(const StreamOp& op, int it, int 
   for (int b = 0; b < R; ++b) P += Hq * ((__ldcg(seq_lens + b) + S + 63) >> 6);
   const int Ge = min(op.act, P);
   if (c >= Ge) return;
-  const int lo = static_cast<int>(static_cast<long long>(c) * P / Ge);
-  const int hi = static_cast<int>(static_cast<long long>(c + 1) * P / Ge);
+  const int lo = static_cast<int>(static_cast<unsigned>(c) * static_cast<unsigned>(P) / static_cast<unsigned>(Ge));
+  const int hi = static_cast<int>(static_cast<unsigned>(c + 1) * static_cast<unsigned>(P) / static_cast<unsigned>(Ge));
   LlmAttnCur cu;  // compute cursor
   {
     int base = 0;
@@ -1875,9 +1876,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         if (op.kind == kOpRow) {
           // one token row (or schedule row) per CTA; a grid smaller than the 128-row tile (several engines side by side,
           // each on its share of the SMs: the ImageNet sampler) takes its rows round-robin
-          row_op<FAM>(prog, op, it, c, tid, red, smem_a);
-          for (int r = c + G; r < 128; r += G) {
-            epi_bar();  // the reduction scratch of the previous row is dead
+          for (int r = c; r < 128; r += G) {
+            if (r != c) epi_bar();  // the reduction scratch of the previous row is dead
             row_op<FAM>(prog, op, it, r, tid, red, smem_a);
           }
         } else if constexpr (FAM == kStreamFamLlm) {

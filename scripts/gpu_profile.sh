@@ -27,6 +27,11 @@ echo "attn capture rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_conv_kernel -s 20 -c 3 -f \
     -o gpurun_out/${TAG}_prof_conv python scripts/ae_bench.py --bs 1 --reps 1 > gpurun_out/${TAG}_ncu_conv.log 2>&1
 echo "conv capture rc=$?"
+# bs = 8 (M = 1024 rows, tensor-bound): launch list of prefill + one AR step
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
+    --log-file gpurun_out/${TAG}_bs8_launches.csv python bench.py --bs 8 --steps 1 --warmup 0 --ar-steps 1 --graph 0 \
+    --no-cpu-baseline --no-gpu-reference --no-roofline > gpurun_out/${TAG}_ncu_bs8.log 2>&1
+echo "bs8 launch list rc=$?"
 # ImageNet class-conditional path (B-16x, bs 64): launch list of the first AR positions
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv \
     --log-file gpurun_out/${TAG}_imagenet_launches.csv python scripts/imagenet_bench.py --bs 64 --reps 1 --no-warmup \
