@@ -19,7 +19,10 @@ KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):   # already exported on the GPU box (scripts/gpu_profile.sh): ncu -i X.ncu-rep --page raw --csv
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr, units = rows[hdr_i], rows[hdr_i + 1]
