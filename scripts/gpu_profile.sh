@@ -41,6 +41,9 @@ capture stream bd_stream_kernel 0 2 1 $BENCH
 capture gemm bd_gemm_kernel 4 2 0 $BENCH
 capture attn bd_attn_kernel 2 1 0 $BENCH
 capture conv bd_conv_kernel 20 2 0 python scripts/ae_bench.py --bs 1 --reps 1
+# the CTA-pair GEMM at M = 1024 rows (bs = 8): three launches of the head's Linears inside the first evaluations
+capture gemm2 bd_gemm2_kernel 60 3 0 python bench.py --bs 8 --steps 1 --warmup 0 --ar-steps 1 --graph 0 \
+    --no-cpu-baseline --no-gpu-reference --no-roofline
 
 # bs = 8 (M = 1024 rows, tensor-bound): launch list of prefill + one AR step
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
