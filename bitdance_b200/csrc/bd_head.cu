@@ -459,6 +459,7 @@ static int head_sample_stream(const bd_head_weights_t& w, const float* cond, con
 
   static thread_local StreamProgram prog;
   prog = StreamProgram{};
+  prog.family = G < 128 ? kStreamFamHeadSmall : kStreamFamHead;
   prog.M = M;
   prog.n_ctas = G;
   prog.rows_x = nx;

@@ -127,7 +127,20 @@ __device__ __forceinline__ float4 ldg_f4(const void* p) { return __ldg(reinterpr
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
 // LN statistics + modulate of a row held as packed bf16; writes `a` blocked (or to smem floats when a_smem != nullptr).
-template <int NV>
+// TPR: threads per row — 128 (the 4 executor warps on one row, block reductions through `red`) or 32 (one warp per row,
+// shuffle reductions, `tid` = lane: the small-model mode where a CTA owns several rows of the tile, see kStreamFamHeadSmall)
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* red, int tid) {
+  if constexpr (TPR == 32) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  } else {
+    return epi_sum(v, red, tid);
+  }
+}
+
+template <int NV, int TPR = 128>
 __device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, const uint4 (&vb)[NV], float sum, float* red,
                                            const float* ln_w, const float* ln_b, float* a_smem) {
   const int D = op.N, nvec = D / 8;
@@ -138,7 +151,7 @@ __device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, c
   float4 lw[NV][2], lb[NV][2];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = tid + i * 128;
+    const int c = tid + i * TPR;
     scr[i] = shr[i] = make_uint4(0, 0, 0, 0);
     lw[i][0] = lw[i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
     lb[i][0] = lb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -153,11 +166,11 @@ __device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, c
       }
     }
   }
-  const float mean = epi_sum(sum, red, tid) / static_cast<float>(D);
+  const float mean = row_sum<TPR>(sum, red, tid) / static_cast<float>(D);
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = tid + i * 128;
+    const int c = tid + i * TPR;
     if (c < nvec) {
       float v[8];
       bf16x8_to_f(vb[i], v);
@@ -168,11 +181,11 @@ __device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, c
       }
     }
   }
-  const float rstd = rsqrtf(epi_sum(sq, red, tid) / static_cast<float>(D) + op.f0);
+  const float rstd = rsqrtf(row_sum<TPR>(sq, red, tid) / static_cast<float>(D) + op.f0);
   uint8_t* a = reinterpret_cast<uint8_t*>(op.o0);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = tid + i * 128;
+    const int c = tid + i * TPR;
     if (c < nvec) {
       float v[8], sc[8], sh[8], o[8];
       bf16x8_to_f(vb[i], v);
@@ -198,7 +211,7 @@ __device__ __forceinline__ void row_ln_mod(const StreamOp& op, int r, int tid, c
 
 // h = bf16(h + bf16(bf16(sum_s partial_s + bias) * gate)), fixed summation order s = 0, 1, ... (deterministic); returns
 // the row as packed bf16 + its sum. Loads: two splits per batch, then [h, gate, bias] in one batch.
-template <int NV, int SC>  // SC: compile-time split count (0 = run time)
+template <int NV, int SC, int TPR = 128>  // SC: compile-time split count (0 = run time)
 __device__ __forceinline__ float row_splitk(const StreamOp& op, int M, int r, int tid, uint4 (&vb)[NV]) {
   const int D = op.N, nvec = D / 8, S = SC > 0 ? SC : op.i0;
   const float* part = reinterpret_cast<const float*>(op.p0) + static_cast<long long>(r) * D;
@@ -211,7 +224,7 @@ __device__ __forceinline__ float row_splitk(const StreamOp& op, int M, int r, in
     float4 x0[NV], x1[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c = tid + i * 128;
+      const int c = tid + i * TPR;
       x0[i] = x1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < nvec) {
         const float* q = part + s * sstride + c * 8;
@@ -246,7 +259,7 @@ __device__ __forceinline__ float row_splitk(const StreamOp& op, int M, int r, in
   uint4 hraw[NV], graw[NV], braw[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = tid + i * 128;
+    const int c = tid + i * TPR;
     hraw[i] = graw[i] = braw[i] = make_uint4(0, 0, 0, 0);
     if (c < nvec) {
       hraw[i] = ldcg_u4(h + c * 8);
@@ -257,7 +270,7 @@ __device__ __forceinline__ float row_splitk(const StreamOp& op, int M, int r, in
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = tid + i * 128;
+    const int c = tid + i * TPR;
     vb[i] = make_uint4(0, 0, 0, 0);
     if (c < nvec) {
       float b[8], g[8], res[8], v[8];
@@ -325,7 +338,7 @@ __device__ __forceinline__ void row_final_linear(const StreamOp& op, int M, int 
   }
 }
 
-template <int NV>
+template <int NV, int TPR = 128>
 __device__ __forceinline__ void row_op_ln_family(const StreamProgram& prog, const StreamOp& op, int it, int r, int tid,
                                                  float* red, uint8_t* scratch) {
   const int M = prog.M;
@@ -337,7 +350,7 @@ __device__ __forceinline__ void row_op_ln_family(const StreamProgram& prog, cons
     const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(op.p0) + static_cast<long long>(r) * op.N;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c = tid + i * 128;
+      const int c = tid + i * TPR;
       vb[i] = c < nvec ? ldcg_u4(h + c * 8) : make_uint4(0, 0, 0, 0);
     }
     float sum = 0.f;
@@ -348,20 +361,21 @@ __device__ __forceinline__ void row_op_ln_family(const StreamProgram& prog, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum += v[j];
     }
-    row_ln_mod<NV>(op, r, tid, vb, sum, red, ln_w, ln_b, nullptr);
+    row_ln_mod<NV, TPR>(op, r, tid, vb, sum, red, ln_w, ln_b, nullptr);
     return;
   }
   // h = bf16(h + bf16(bf16(sum_s partial_s + bias) * gate));  then the LayerNorm-modulate that follows in the network
   // (TransBlock.forward flow_head_parallel_x.py:242-252; FinalLayer.forward :169-173 for kRowFinal)
   float sum;
-  if (op.i0 == 4) sum = row_splitk<NV, 4>(op, M, r, tid, vb);
-  else if (op.i0 == 2) sum = row_splitk<NV, 2>(op, M, r, tid, vb);
-  else if (op.i0 == 1) sum = row_splitk<NV, 1>(op, M, r, tid, vb);
-  else sum = row_splitk<NV, 0>(op, M, r, tid, vb);
+  if (op.i0 == 4) sum = row_splitk<NV, 4, TPR>(op, M, r, tid, vb);
+  else if (op.i0 == 2) sum = row_splitk<NV, 2, TPR>(op, M, r, tid, vb);
+  else if (op.i0 == 1) sum = row_splitk<NV, 1, TPR>(op, M, r, tid, vb);
+  else sum = row_splitk<NV, 0, TPR>(op, M, r, tid, vb);
   if (op.sub == kRowSplitkLnMod) {
-    row_ln_mod<NV>(op, r, tid, vb, sum, red, ln_w, ln_b, nullptr);
+    row_ln_mod<NV, TPR>(op, r, tid, vb, sum, red, ln_w, ln_b, nullptr);
     return;
   }
+  if constexpr (TPR != 128) return;  // (the final row needs the whole block: never dispatched in warp mode)
   // final layer: LayerNorm without affine; a stays in shared memory (aliasing the A ring), then the 5120 -> C Linear
   float* arow = reinterpret_cast<float*>(scratch);
   row_ln_mod<NV>(op, r, tid, vb, sum, red, nullptr, nullptr, arow);
@@ -490,7 +504,7 @@ template <int FAM>
 __device__ __forceinline__ void row_op(const StreamProgram& prog, const StreamOp& op, int it, int r, int tid, float* red,
                                        uint8_t* scratch) {
   const int M = prog.M;
-  if constexpr (FAM == kStreamFamHead) {
+  if constexpr (FAM != kStreamFamLlm) {
   switch (op.sub) {
     case kRowCastCond: {  // p0 fp32 [M, N] (kernel input) -> o0 blocked bf16
       if (r >= M) return;
@@ -1876,9 +1890,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
         if (op.kind == kOpRow) {
           // one token row (or schedule row) per CTA; a grid smaller than the 128-row tile (several engines side by side,
           // each on its share of the SMs: the ImageNet sampler) takes its rows round-robin
-          for (int r = c; r < 128; r += G) {
-            if (r != c) epi_bar();  // the reduction scratch of the previous row is dead
-            row_op<FAM>(prog, op, it, r, tid, red, smem_a);
+          bool done = false;
+          if constexpr (FAM == kStreamFamHeadSmall) {
+            if ((op.sub == kRowLnMod || op.sub == kRowSplitkLnMod) && op.N <= 32 * kRowVec * 8) {
+              // one warp per row: the CTA's rows c, c + G, ... are dealt to its 4 executor warps (no block barrier inside)
+              for (int r = c + (tid >> 5) * G; r < prog.M; r += 4 * G)
+                row_op_ln_family<kRowVec, 32>(prog, op, it, r, tid & 31, nullptr, nullptr);
+              done = true;
+            }
+          }
+          if (!done) {
+            for (int r = c; r < 128; r += G) {
+              if (r != c) epi_bar();  // the reduction scratch of the previous row is dead
+              row_op<FAM>(prog, op, it, r, tid, red, smem_a);
+            }
           }
         } else if constexpr (FAM == kStreamFamLlm) {
           if (op.kind == kOpLlmRope) {
@@ -2001,6 +2026,8 @@ int stream_launch(const StreamProgram& prog_in, cudaStream_t stream) {
                                        StreamSmem::kTotal));
       BD_CUDA_TRY(cudaFuncSetAttribute(bd_stream_kernel<kStreamFamLlm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        StreamSmem::kTotal));
+      BD_CUDA_TRY(cudaFuncSetAttribute(bd_stream_kernel<kStreamFamHeadSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       StreamSmem::kTotal));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -2016,8 +2043,9 @@ int stream_launch(const StreamProgram& prog_in, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ++g_launch_count;
-  BD_REQUIRE(prog.family == kStreamFamHead || prog.family == kStreamFamLlm);
+  BD_REQUIRE(prog.family == kStreamFamHead || prog.family == kStreamFamLlm || prog.family == kStreamFamHeadSmall);
   if (prog.family == kStreamFamLlm) BD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bd_stream_kernel<kStreamFamLlm>, prog));
+  else if (prog.family == kStreamFamHeadSmall) BD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bd_stream_kernel<kStreamFamHeadSmall>, prog));
   else BD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bd_stream_kernel<kStreamFamHead>, prog));
   return BD_OK;
 }

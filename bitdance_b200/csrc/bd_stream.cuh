@@ -116,7 +116,10 @@ struct StreamOp {
 };
 constexpr int kTabSlots = 8;
 
-enum : int { kStreamFamHead = 0, kStreamFamLlm = 1 };  // which instance of the kernel runs the program (its executors)
+// which instance of the kernel runs the program (its executors). kStreamFamHeadSmall = the head's program on a grid smaller
+// than the 128-row tile (several engines side by side, small models): a CTA owns several rows, so the LayerNorm row ops run
+// one WARP per row (4 rows in flight per CTA) instead of one row per CTA at a time.
+enum : int { kStreamFamHead = 0, kStreamFamLlm = 1, kStreamFamHeadSmall = 2 };
 
 struct StreamProgram {
   int family;
