@@ -929,6 +929,127 @@ __device__ __forceinline__ void attn_unit(const StreamOp& op, int unit, int tid,
   epi_bar();  // tiles (aliasing the A ring) dead
 }
 
+// One WARP per (sequence, head) unit when a block is at most 16 tokens and head_dim is 64 (the ImageNet models on a small
+// grid, kStreamFamHeadSmall): Q, K and V are 16 rows of 128 bytes each, copied by the warp itself (the rows keep the blocked
+// buffer's swizzle), one m16 query tile x 16 keys; no block barrier, so a CTA has 4 units in flight. Same arithmetic as
+// attn_unit. wsm: the warp's 6 KB of the A ring.
+__device__ __forceinline__ void attn_unit_warp64(const StreamOp& op, int unit, int lane, uint8_t* wsm) {
+  constexpr int HD = 64;
+  const int D = op.N, pn = op.i0, H = D / HD;
+  const int seq = unit / H, hd = unit % H;
+  const int row0 = seq * pn;
+  uint8_t* sQ = wsm;
+  uint8_t* sK = wsm + 2048;
+  uint8_t* sV = wsm + 4096;
+  const uint8_t* qkv = reinterpret_cast<const uint8_t*>(op.p0);
+  __syncwarp();  // the previous unit's reads of these tiles are complete
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    const int kb = (which * D + hd * HD) / 64;
+    const uint8_t* src = qkv + static_cast<long long>(kb) * kSlotBytes + row0 * 128;
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = lane + 32 * k, r = i >> 3;
+      v[k] = r < pn ? ldcg_u4(src + r * 128 + (i & 7) * 16) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = lane + 32 * k;
+      *reinterpret_cast<uint4*>(wsm + which * 2048 + (i >> 3) * 128 + (i & 7) * 16) = v[k];
+    }
+  }
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  const float scale_log2 = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;
+  float s[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ks += 2) {
+    uint32_t a0[4], a1[4], bk[2][4];
+    s_ldmatrix_x4(a0, smem_u32(sQ + s_tile_off(lane & 15, 2 * ks + (lane >> 4), row0)));
+    s_ldmatrix_x4(a1, smem_u32(sQ + s_tile_off(lane & 15, 2 * ks + 2 + (lane >> 4), row0)));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) s_ldmatrix_x4(bk[j], smem_u32(sK + s_tile_off(8 * j + (lane & 7), 2 * ks + (lane >> 3), row0)));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) s_mma_16816_nv(s[j], a0, bk[j][0], bk[j][1]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) s_mma_16816_nv(s[j], a1, bk[j][2], bk[j][3]);
+  }
+  float mx[2] = {-FLT_MAX, -FLT_MAX};
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int key = 8 * j + 2 * t + (i & 1);
+      const float v = key < pn ? s[j][i] * scale_log2 : -FLT_MAX;
+      s[j][i] = v;
+      mx[i >> 1] = fmaxf(mx[i >> 1], v);
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+  float l[2] = {0.f, 0.f};
+  uint32_t pa[4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      e[i] = (s[j][i] == -FLT_MAX) ? 0.f : exp2f(s[j][i] - mx[i >> 1]);
+      l[i >> 1] += e[i];
+    }
+    pa[2 * j] = s_pack_bf16(e[0], e[1]);
+    pa[2 * j + 1] = s_pack_bf16(e[2], e[3]);
+  }
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
+  {
+    uint32_t bv[HD / 16][4];
+#pragma unroll
+    for (int n = 0; n < HD / 16; ++n)
+      s_ldmatrix_x4_trans(bv[n], smem_u32(sV + s_tile_off((lane & 7) + 8 * ((lane >> 3) & 1), 2 * n + (lane >> 4), row0)));
+#pragma unroll
+    for (int n = 0; n < HD / 16; ++n) {
+      s_mma_16816_nv(o_acc[2 * n], pa, bv[n][0], bv[n][1]);
+      s_mma_16816_nv(o_acc[2 * n + 1], pa, bv[n][2], bv[n][3]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  __syncwarp();  // every lane's ldmatrix of Q is complete: O takes the Q tile's place
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qrow = g + 8 * r;
+    const float inv = l[r] > 0.f ? 1.0f / l[r] : 0.f;
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n)
+      *reinterpret_cast<uint32_t*>(sQ + s_tile_off(qrow, n, row0) + 4 * t) =
+          s_pack_bf16(o_acc[n][2 * r] * inv, o_acc[n][2 * r + 1] * inv);
+  }
+  __syncwarp();
+  uint8_t* out = reinterpret_cast<uint8_t*>(op.o0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {  // 16 rows x 4 sectors of 32 bytes
+    const int i = lane + 32 * k, rr = i >> 2, sec = i & 3;
+    if (rr >= pn) continue;
+    const uint8_t* src = sQ + rr * 128 + sec * 32;
+    const uint4 a = *reinterpret_cast<const uint4*>(src), b = *reinterpret_cast<const uint4*>(src + 16);
+    st_global_32B(out + static_cast<long long>((hd * HD) / 64) * kSlotBytes + (row0 + rr) * 128 + sec * 32, a, b);
+  }
+}
+
 // The op descriptor is a copy of a kernel parameter: left alone, the compiler re-reads its fields from the constant bank
 // with a run-time index wherever they are used (an IMAD + LDC chain in front of every use in the tile loop). pin() makes
 // the value opaque, so it stays in a register.
@@ -1892,7 +2013,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           // each on its share of the SMs: the ImageNet sampler) takes its rows round-robin
           bool done = false;
           if constexpr (FAM == kStreamFamHeadSmall) {
-            if ((op.sub == kRowLnMod || op.sub == kRowSplitkLnMod) && op.N <= 32 * kRowVec * 8) {
+            if ((op.sub == kRowLnMod || op.sub == kRowSplitkLnMod) && op.N <= 32 * kRowVec * 8 && !(prog.dbg_mode & 512)) {
               // one warp per row: the CTA's rows c, c + G, ... are dealt to its 4 executor warps (no block barrier inside)
               for (int r = c + (tid >> 5) * G; r < prog.M; r += 4 * G)
                 row_op_ln_family<kRowVec, 32>(prog, op, it, r, tid & 31, nullptr, nullptr);
@@ -1917,7 +2038,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           }
         } else if (op.kind == kOpAttn) {
           const int units = (prog.M / op.i0) * (op.N / op.K);
-          for (int u = c; u < units; u += G) {
+          bool done = false;
+          if constexpr (FAM == kStreamFamHeadSmall) {
+            if (op.K == 64 && op.i0 <= 16 && !(prog.dbg_mode & 256)) {  // one warp per unit (mode 256: measurement, off)
+              for (int u = c + (tid >> 5) * G; u < units; u += 4 * G)
+                attn_unit_warp64(op, u, tid & 31, smem_a + (tid >> 5) * 6144);
+              done = true;
+            }
+          }
+          for (int u = c; u < units && !done; u += G) {
             if (op.K == 128) attn_unit<128>(op, u, tid, smem_a, aux_bar, aux_uses & 1u);
             else attn_unit<64>(op, u, tid, smem_a, aux_bar, aux_uses & 1u);
             ++aux_uses;

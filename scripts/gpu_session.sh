@@ -23,7 +23,9 @@ for step in "$@"; do
     ab)       timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab.txt 2>&1 ;;
     ab_r01)   BD_LIB_PATH=$PWD/ab/libbitdance_b200_r01.so timeout 900 python scripts/head_ab.py >> gpurun_out/${TAG}_head_ab_r01.txt 2>&1 ;;
     diag)     timeout 600 python scripts/head_diag.py > gpurun_out/${TAG}_head_diag.txt 2>&1 ;;
-    imagenet) timeout 1200 python scripts/imagenet_bench.py > gpurun_out/${TAG}_imagenet_bench.txt 2>&1 ;;
+    imagenet) timeout 1200 python scripts/imagenet_bench.py --bs 64 --modes 0 256 512 768 > gpurun_out/${TAG}_imagenet_bench.txt 2>&1
+              timeout 600 python scripts/imagenet_bench.py --bs 64 256 --head-engines 0 >> gpurun_out/${TAG}_imagenet_bench.txt 2>&1 ;;
+    imagenettest) timeout 900 python -m pytest tests/test_imagenet_gpu.py tests/test_head_gpu.py -m gpu -q -s 2>&1 | grep -v "^    " | tail -60 > gpurun_out/${TAG}_test_imagenet.log ;;
     ae)       timeout 900 python scripts/ae_bench.py > gpurun_out/${TAG}_ae_bench.txt 2>&1 ;;
     bench)    timeout 1500 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
     benchref) timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err ;;

@@ -29,12 +29,15 @@ def main():
     ap.add_argument("--latent-dim", type=int, default=32)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--no-warmup", action="store_true", help="profiling (ncu launch list): no warm-up pass")
+    ap.add_argument("--head-engines", type=int, default=None, help="persistent head engines side by side (0: multi-kernel path)")
+    ap.add_argument("--modes", type=int, nargs="+", default=[0],
+                    help="bd_stream_set_tuning mode bits per run (256: block-wide attention units, 512: block-wide row ops)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     cfg = dict(MODELS[args.model], latent_dim=args.latent_dim, down_size=16, patch_size=1, resolution=256, cls_token_num=64,
                num_classes=1000, parallel_num=args.parallel_num, parallel_mode="patch", time_shift=1.0)
     sd = _gpu_state_dict(imagenet_spec(cfg), 7, dev)
-    eng = ImageNetEngine(sd, cfg, ae=None, device=dev)
+    eng = ImageNetEngine(sd, cfg, ae=None, device=dev, head_engines=args.head_engines)
     del sd
     peaks = {}
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -46,7 +49,10 @@ def main():
     Dh, nb, na = cfg["diff_dim"], cfg["diff_layers"], cfg["diff_adanln_layers"]
     p_head = nb * (4 * Dh * Dh + 3 * Dh * int(Dh * 1.5) * 1) + na * 6 * Dh * Dh + 2 * Dh * Dh + dim * Dh + Dh * Dh
     hw, pn = eng.h * eng.w, eng.pn
-    for bs in args.bs:
+    from bitdance_b200 import _lib
+    lib = _lib.load()
+    for bs, mode in [(b, m) for b in args.bs for m in args.modes]:
+        lib.bd_stream_set_tuning(5, 2, mode)
         ids = torch.randint(0, 1000, (bs,), device=dev)
         if not args.no_warmup:
             eng.sample_tokens(ids, args.steps, args.cfg)   # warm-up (allocations, first launches)
@@ -60,7 +66,7 @@ def main():
         ms = e0.elapsed_time(e1) / args.reps
         rows = 2 * bs * pn                                                          # token rows per AR position (CFG)
         flops = (hw // pn) * (2.0 * p_dec * rows + (args.steps + 1) * 2.0 * p_head * rows)
-        print(json.dumps({"model": args.model, "parallel_num": pn, "bs": bs, "sampling_steps": args.steps, "cfg": args.cfg,
+        print(json.dumps({"model": args.model, "parallel_num": pn, "bs": bs, "head_engines": len(eng._side), "mode": mode, "sampling_steps": args.steps, "cfg": args.cfg,
                           "images_per_s": bs / (ms / 1e3), "ms_per_batch": ms, "ms_per_ar_position": ms / (hw // pn),
                           "rows_per_position": rows, "tflops": flops / 1e12 / (ms / 1e3),
                           "frac_of_sustained_bf16": flops / 1e12 / (ms / 1e3) / peak,
