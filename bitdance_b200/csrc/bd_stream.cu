@@ -291,14 +291,16 @@ __device__ __forceinline__ float row_splitk(const StreamOp& op, int M, int r, in
 }
 
 // final layer tail: a (bf16 values, fp32 in shared memory) -> o_c = bf16(sum_d a_d Wf[c,d] + bias_c); optional 2*sigmoid-1
+template <int TPR = 128>
 __device__ __forceinline__ void row_final_linear(const StreamOp& op, int M, int it, int r, int tid, const float* arow) {
   const int D = op.N, C = op.i1;
   const __nv_bfloat16* Wf = reinterpret_cast<const __nv_bfloat16*>(op.p1);
   const __nv_bfloat16* bfin = reinterpret_cast<const __nv_bfloat16*>(op.p2);
   float* pred = reinterpret_cast<float*>(op.o0);
   float* trace = reinterpret_cast<float*>(op.o2);
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int c0 = warp * 8; c0 < C; c0 += 32) {  // 8 output channels per warp and round: 8 independent loads per step
+  const int warp = TPR == 128 ? (tid >> 5) : 0, lane = tid & 31;
+  constexpr int kCStep = TPR == 128 ? 32 : 8;  // warp mode: the one warp takes every group of 8 channels in turn
+  for (int c0 = warp * 8; c0 < C; c0 += kCStep) {  // 8 output channels per warp and round: 8 independent loads per step
     float acc[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc[u] = 0.f;
@@ -375,13 +377,15 @@ __device__ __forceinline__ void row_op_ln_family(const StreamProgram& prog, cons
     row_ln_mod<NV, TPR>(op, r, tid, vb, sum, red, ln_w, ln_b, nullptr);
     return;
   }
-  if constexpr (TPR != 128) return;  // (the final row needs the whole block: never dispatched in warp mode)
-  // final layer: LayerNorm without affine; a stays in shared memory (aliasing the A ring), then the 5120 -> C Linear
+  // final layer: LayerNorm without affine; a stays in shared memory (aliasing the A ring; warp mode: the warp's own
+  // slice), then the D -> C Linear
   float* arow = reinterpret_cast<float*>(scratch);
-  row_ln_mod<NV>(op, r, tid, vb, sum, red, nullptr, nullptr, arow);
-  epi_bar();
-  row_final_linear(op, M, it, r, tid, arow);
-  epi_bar();  // arow (aliasing the A ring) is dead before anything else may touch it
+  row_ln_mod<NV, TPR>(op, r, tid, vb, sum, red, nullptr, nullptr, arow);
+  if constexpr (TPR == 128) epi_bar();
+  else __syncwarp();
+  row_final_linear<TPR>(op, M, it, r, tid, arow);
+  if constexpr (TPR == 128) epi_bar();  // arow (aliasing the A ring) is dead before anything else may touch it
+  else __syncwarp();
 }
 
 // Qwen3 residual add + RMSNorm of token row r with the loads of every phase issued together (see the note at the top of
@@ -2013,10 +2017,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) bd_stream_kernel(const __gr
           // each on its share of the SMs: the ImageNet sampler) takes its rows round-robin
           bool done = false;
           if constexpr (FAM == kStreamFamHeadSmall) {
-            if ((op.sub == kRowLnMod || op.sub == kRowSplitkLnMod) && op.N <= 32 * kRowVec * 8 && !(prog.dbg_mode & 512)) {
-              // one warp per row: the CTA's rows c, c + G, ... are dealt to its 4 executor warps (no block barrier inside)
+            if ((op.sub == kRowLnMod || op.sub == kRowSplitkLnMod || op.sub == kRowFinal) && op.N <= 32 * kRowVec * 8 &&
+                !(prog.dbg_mode & 512)) {
+              // one warp per row: the CTA's rows c, c + G, ... are dealt to its 4 executor warps (no block barrier inside;
+              // the final row's activations live in the warp's own 6 KB of the A ring)
               for (int r = c + (tid >> 5) * G; r < prog.M; r += 4 * G)
-                row_op_ln_family<kRowVec, 32>(prog, op, it, r, tid & 31, nullptr, nullptr);
+                row_op_ln_family<kRowVec, 32>(prog, op, it, r, tid & 31, nullptr, smem_a + 24576 + (tid >> 5) * 6144);
               done = true;
             }
           }
