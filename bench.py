@@ -126,6 +126,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # this arm is host-only: hide the GPUs before anything initialises CUDA, so that the reference (and the libraries it
+    # imports: flash_attn has no CPU backend) sees the same CPU-only process it is tested in
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
     threads = os.cpu_count() or 1
     B, S = args.bs, args.sampling_steps
     try:

@@ -86,8 +86,16 @@ def import_reference():
     if REF not in sys.path:
         sys.path.append(REF)  # the reference's own `utils.fs` etc. stay importable, behind this repo's packages
 
-    if not torch.cuda.is_available():
-        fh.flash_attn_func = _eager_flash  # shim A (CPU); on a GPU the reference keeps the real flash_attn kernel
+    # shim A, per call: CPU tensors (flash_attn has no CPU backend) -> eager softmax attention; CUDA tensors keep the real
+    # flash_attn kernel (a GPU box runs BOTH reference arms in one process: GPU-eager and the host-core baseline)
+    _real_flash = getattr(fh, "flash_attn_func", None)
+
+    def _flash(q, k, v, *a, **kw):
+        if q.is_cuda and _real_flash is not None and _real_flash is not _eager_flash:
+            return _real_flash(q, k, v, *a, **kw)
+        return _eager_flash(q, k, v, causal=bool(kw.get("causal", a[2] if len(a) > 2 else False)))
+
+    fh.flash_attn_func = _flash
     from transformers import DynamicCache
     from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
 
