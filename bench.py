@@ -263,9 +263,12 @@ def main():
         assert len(imgs) == B and imgs[0].size == (args.width, args.height)
         if world > 1:   # the finished (packed, 16 KB / image) token grids of every rank, one all-gather per batch
             from bitdance_b200 import parallel
-            allg = parallel.gather_token_grids(pipe.last_packed_tokens)
-            collectives["token_grid_all_gather"] = {"bytes_per_rank": int(pipe.last_packed_tokens.numel() * 4),
-                                                    "gathered_shape": list(allg.shape)}
+            try:
+                allg = parallel.gather_token_grids(pipe.last_packed_tokens)
+                collectives["token_grid_all_gather"] = {"bytes_per_rank": int(pipe.last_packed_tokens.numel() * 4),
+                                                        "gathered_shape": list(allg.shape)}
+            except Exception as e:   # never lose the bench line to the optional exchange step
+                collectives["token_grid_all_gather"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     ids_dev = ids_host.to(dev)
 

@@ -85,7 +85,10 @@ class T2IEngine:
     def weight_tensors(self):
         """Every prepacked weight tensor the engine streams (decoder, head, projector, tokenizer) — the set a start-up
         ``parallel.broadcast_tensors`` ships from rank 0 instead of N disk reads."""
-        ts = [t for t in self.llm._keep if t is not None] + [t for t in self.head._keep if t is not None]
+        # floating-point payload only: llm._keep also holds the per-layer DEVICE-POINTER table of the one-launch AR block
+        # (int64 addresses of this process's allocations) — shipping rank 0's addresses would corrupt the receivers
+        ts = [t for t in self.llm._keep if t is not None and t.is_floating_point()]
+        ts += [t for t in self.head._keep if t is not None and t.is_floating_point()]
         ts += [self.fc1_w.data, self.fc1_b, self.fc2_w.data, self.fc2_b]
         if self.ae is not None:
             for c in self.ae.convs.values():
