@@ -91,7 +91,7 @@ AR_STEPS_PER_IMAGE = {"BitDance-14B-64x": 64, "BitDance-14B-16x": 256}
 
 
 def reference_sample(model: str, device: str, n_warm: int, n_timed: int, S: int, guidance: float, height: int, bs: int,
-                     threads: int | None = None, with_decode: bool = True):
+                     threads: int | None = None, with_decode: bool = True, budget_s: float | None = None):
     """Times the reference's own ``BitDanceT2IPipeline.gen_image`` (oracle/ref_runner.py: its classes, its loop, random-init
     weights of the named architecture, bf16 autocast as in ``generate()``) on a BOUNDED sample: the causal prefill of the
     cond + uncond prompts, then ``n_warm + n_timed`` AR steps of the unmodified loop (each = 51-evaluation DiffHead.sample
@@ -105,6 +105,19 @@ def reference_sample(model: str, device: str, n_warm: int, n_timed: int, S: int,
     if device == "cpu" and threads:
         torch.set_num_threads(threads)
     pipe, info = rr.build_pipeline(model, device, with_ae=with_decode)
+    note = ""
+    if budget_s is not None and n_warm + n_timed > 2:
+        # keep the whole arm within a few minutes whatever --steps / --warmup the caller passes and however slow the host is:
+        # one calibration call of the unmodified loop (1 AR step, cold: first touch of 33 GB of weights, autocast casts)
+        # sizes the sample; it counts as warm-up
+        cal = rr.run_bounded(pipe, info, n_ar=1, image_px=height, guidance=guidance, S=S, num_images=bs)
+        fit = max(2, int(budget_s / max(cal["ar_s"][0] + 1e-9, 1e-3)))
+        if fit < n_warm + n_timed:
+            new_timed = max(1, min(n_timed, fit - 1))
+            new_warm = max(1, min(n_warm, fit - new_timed))
+            note = (f" [bounded: calibration step {cal['ar_s'][0]:.2f} s, {budget_s:.0f} s budget -> {new_warm} warm-up + "
+                    f"{new_timed} timed steps instead of {n_warm} + {n_timed}]")
+            n_warm, n_timed = new_warm, new_timed
     run = rr.run_bounded(pipe, info, n_ar=n_warm + n_timed, image_px=height, guidance=guidance, S=S, num_images=bs)
     timed = run["ar_s"][n_warm:]
     ar = statistics.median(timed)
@@ -114,8 +127,8 @@ def reference_sample(model: str, device: str, n_warm: int, n_timed: int, S: int,
     desc = (f"unmodified reference gen_image on {device} ({'all ' + str(threads) + ' host threads, ' if device == 'cpu' else ''}"
             f"bf16 autocast, random-init {model}): prefill {run['prefill_s']:.2f} s + {n_warm} warm-up + {n_timed} timed AR steps "
             f"(median {ar:.3f} s, all {[round(x, 3) for x in run['ar_s']]}) + decode {dec:.2f} s; image = prefill + {steps} x "
-            f"median + decode (extrapolated)")
-    out = dict(images_per_s=bs / sec_per_batch, ar_step_s=ar, prefill_s=run["prefill_s"], decode_s=dec, build_s=info["build_s"],
+            f"median + decode (extrapolated){note}")
+    out = dict(n_warm=n_warm, n_timed=n_timed, images_per_s=bs / sec_per_batch, ar_step_s=ar, prefill_s=run["prefill_s"], decode_s=dec, build_s=info["build_s"],
                sample=desc, measured_s=run["total_s"] + dec)
     del pipe, info
     return out
@@ -132,7 +145,8 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     B, S = args.bs, args.sampling_steps
     try:
-        r = reference_sample(args.model, "cpu", args.warmup, args.steps, S, args.guidance, args.height, B, threads)
+        r = reference_sample(args.model, "cpu", args.warmup, args.steps, S, args.guidance, args.height, B, threads,
+                             budget_s=150.0)
     except Exception as e:  # the shipped copy is missing (oracle/make_ref.py not run) or the host cannot hold the model
         print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"[:300]}))
         return
@@ -143,7 +157,8 @@ def run_reference_arm(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
             "config": {"workload": f"{args.model} random-init, {args.height}x{args.width}, {steps} AR steps, bs={B}, "
                                    f"CFG {args.guidance}, S={S} (+1), synthetic 64-token prompt",
-                       "extrapolated": True, "step": "one AR step of the unmodified loop", "ms_per_ar_step": 1e3 * r["ar_step_s"],
+                       "extrapolated": True, "step": "one AR step of the unmodified loop",
+                       "ar_steps_run": {"warmup": r["n_warm"], "timed": r["n_timed"]}, "ms_per_ar_step": 1e3 * r["ar_step_s"],
                        "prefill_ms": 1e3 * r["prefill_s"], "decode_ms": 1e3 * r["decode_s"]},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "reference", "sample": r["sample"]},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
