@@ -239,3 +239,27 @@ class LlmRunner:
             for r in range(r0, r0 + R):
                 cache.host_lens[r] += S
         return out
+
+
+class LmHead:
+    """``Qwen3ForCausalLM.lm_head`` (``nn.Linear(hidden, vocab, bias=False)``; reference call site modeling/mllm.py:845-846)
+    on the tcgen05 weight-streaming GEMM: the [vocab, hidden] matrix is prepacked tile-major once (vocab padded to a
+    multiple of 128 rows with zeros), a decode step is ONE launch that streams it once (1.56 GB for Qwen3-14B).
+    Output is rounded to bf16 — what a bf16 ``nn.Linear`` returns."""
+
+    def __init__(self, weight: torch.Tensor, device="cuda"):
+        w = weight.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+        assert w.dim() == 2
+        self.vocab, self.hidden = w.shape
+        pad = (-self.vocab) % 128
+        if pad:
+            w = torch.cat([w, torch.zeros((pad, self.hidden), dtype=w.dtype, device=w.device)], dim=0)
+        self.w = ops.pack_weight(w)
+
+    @torch.no_grad()
+    def __call__(self, hidden: torch.Tensor) -> torch.Tensor:
+        """hidden [..., hidden] -> logits [..., vocab] bf16"""
+        shp = hidden.shape
+        a = hidden.reshape(-1, shp[-1]).to(torch.bfloat16).contiguous()
+        out = ops.gemm(a, self.w)
+        return out[:, :self.vocab].reshape(*shp[:-1], self.vocab)

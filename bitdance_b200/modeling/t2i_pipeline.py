@@ -44,11 +44,26 @@ def _load_llm_state_dict(model_path: str) -> dict:
 
 
 class _EmbedOnlyLLM:
-    """What callers touch on ``pipe.llm_model``: ``.model.embed_tokens`` (the decoder layers live in the native runner)."""
+    """What callers touch on ``pipe.llm_model``: ``.model.embed_tokens`` and — interleaved text generation only,
+    modeling/mllm.py:845 — ``.lm_head`` (the decoder layers live in the native runner). ``lm_head_weight`` ([vocab, hidden],
+    may stay on the host) is prepacked for the GEMM on first use; with tied embeddings it is the embedding table."""
 
-    def __init__(self, embed_weight: torch.Tensor):
+    def __init__(self, embed_weight: torch.Tensor, lm_head_weight: torch.Tensor | None = None):
         emb = nn.Embedding.from_pretrained(embed_weight, freeze=True)
         self.model = types.SimpleNamespace(embed_tokens=emb)
+        self._lm_head_weight = lm_head_weight
+        self._lm_head = None
+
+    @property
+    def lm_head(self):
+        if self._lm_head is None:
+            if self._lm_head_weight is None:
+                raise AttributeError("this model directory has no lm_head.weight (and tie_word_embeddings is off): "
+                                     "text generation is unavailable")
+            from ..llm import LmHead
+            self._lm_head = LmHead(self._lm_head_weight, device=self.model.embed_tokens.weight.device)
+            self._lm_head_weight = None
+        return self._lm_head
 
 
 class BitDanceT2IPipeline:
@@ -61,7 +76,10 @@ class BitDanceT2IPipeline:
             self.llm_config = json.load(f)
         self.hidden_size = self.llm_config["hidden_size"]
         sd = _load_llm_state_dict(model_path)
-        self.llm_model = _EmbedOnlyLLM(sd["model.embed_tokens.weight"].to(device, torch.bfloat16))
+        head_w = sd.get("lm_head.weight")
+        if head_w is None and self.llm_config.get("tie_word_embeddings", False):
+            head_w = sd["model.embed_tokens.weight"]
+        self.llm_model = _EmbedOnlyLLM(sd["model.embed_tokens.weight"].to(device, torch.bfloat16), head_w)
         llm = LlmRunner(sd, self.llm_config, device=device,
                         max_positions=max(8192, int(self.llm_config.get("max_position_embeddings", 8192))))
         del sd
@@ -92,13 +110,14 @@ class BitDanceT2IPipeline:
 
     @classmethod
     def from_components(cls, *, tokenizer, embed_weight, llm: LlmRunner, ae: VQModel, vision_head: DiffHead,
-                        embed_vision_mlp: MLPconnector, ae_config: dict, vision_head_config: dict, device='cuda'):
+                        embed_vision_mlp: MLPconnector, ae_config: dict, vision_head_config: dict, device='cuda',
+                        lm_head_weight: torch.Tensor | None = None):
         """Assemble a pipeline from already-built parts (tests, synthetic weights)."""
         self = object.__new__(cls)
         self.device, self.tokenizer = device, tokenizer
         self.hidden_size = llm.cfg["hidden_size"]
         self.llm_config = dict(llm.cfg)
-        self.llm_model = _EmbedOnlyLLM(embed_weight.to(device, torch.bfloat16))
+        self.llm_model = _EmbedOnlyLLM(embed_weight.to(device, torch.bfloat16), lm_head_weight)
         self.ae_config, self.vision_head_config = ae_config, vision_head_config
         self.ae, self.vision_head, self.embed_vision_mlp = ae, vision_head, embed_vision_mlp
         self.vae_patch_size = 2 ** (len(ae_config['ddconfig']['ch_mult']) - 1)
@@ -108,7 +127,8 @@ class BitDanceT2IPipeline:
         return self
 
     @classmethod
-    def from_engine(cls, engine: T2IEngine, *, tokenizer, embed_weight, device='cuda'):
+    def from_engine(cls, engine: T2IEngine, *, tokenizer, embed_weight, device='cuda',
+                    lm_head_weight: torch.Tensor | None = None):
         """The public surface over an already-built engine (bench.py: synthetic 14B weights generated on the device, so
         there are no nn.Module copies of them): ``generate`` / ``gen_image`` / ``decode_image`` work as usual; ``ae`` /
         ``vision_head`` / ``embed_vision_mlp`` expose only their native runners."""
@@ -116,7 +136,7 @@ class BitDanceT2IPipeline:
         self.device, self.tokenizer, self.engine = device, tokenizer, engine
         self.hidden_size = engine.D
         self.llm_config = dict(engine.llm.cfg)
-        self.llm_model = _EmbedOnlyLLM(embed_weight.to(device, torch.bfloat16))
+        self.llm_model = _EmbedOnlyLLM(embed_weight.to(device, torch.bfloat16), lm_head_weight)
         self.ae = types.SimpleNamespace(runner=engine.ae)
         self.vision_head = types.SimpleNamespace(runner=engine.head)
         self.embed_vision_mlp = None

@@ -27,7 +27,12 @@ def write_model_dir(path: str, seed: int = 0) -> dict:
                    tie_word_embeddings=False, hidden_act="silu", torch_dtype="bfloat16")
     with open(os.path.join(path, "config.json"), "w") as f:
         json.dump(llm_cfg, f)
-    save_file({k: v.to(torch.bfloat16).contiguous() for k, v in sds["llm"].items()}, os.path.join(path, "model.safetensors"))
+    # lm_head (interleaved text generation): not part of tiny_state_dicts (the goldens predate it); same generator family
+    from bitdance_b200.synth import synth_state_dict
+    lm_head = synth_state_dict({"lm_head.weight": (m["llm"]["vocab_size"], m["llm"]["hidden_size"])}, seed=seed + 9, std=0.05)
+    lm_head = {k: v.to(torch.bfloat16).float() for k, v in lm_head.items()}
+    save_file({k: v.to(torch.bfloat16).contiguous() for k, v in {**sds["llm"], **lm_head}.items()},
+              os.path.join(path, "model.safetensors"))
     write_tokenizer(path, m["llm"]["vocab_size"], m["parallel_num"])
     ae_config = {"ddconfig": m["ae"]}
     with open(os.path.join(path, "ae_config.json"), "w") as f:
@@ -38,4 +43,4 @@ def write_model_dir(path: str, seed: int = 0) -> dict:
         json.dump(head_config, f)
     save_file({k: v.contiguous() for k, v in sds["head"].items()}, os.path.join(path, "vision_head.safetensors"))
     save_file({k: v.contiguous() for k, v in sds["proj"].items()}, os.path.join(path, "projector.safetensors"))
-    return dict(sds=sds, model=m, ae_config=ae_config, head_config=head_config)
+    return dict(sds=sds, model=m, ae_config=ae_config, head_config=head_config, lm_head=lm_head["lm_head.weight"])
