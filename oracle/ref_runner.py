@@ -64,6 +64,34 @@ class StubTokenizer:
         return self.base + 110 + int(tk[8:-2])
 
 
+_TILE = 1 << 22
+_TILES = {}
+
+
+def _fill_normal(p: torch.Tensor, std: float, g=None):
+    """N(0, std) values. torch's CPU normal_ is a serial generator (~10 ns / element: minutes for 14.8 B parameters, all of
+    it box time spent before the measurement starts), so a large HOST tensor is filled with one 4 M-element random tile
+    repeated along the flattened tensor — rows are shifted copies, not equal (4 194 304 is not a multiple of any row
+    length here); the timing baseline does not depend on the values. Small tensors and device tensors draw every element."""
+    if p.device.type != "cpu" or p.numel() <= _TILE:
+        if p.device.type == "cpu":
+            p.copy_((torch.randn(p.shape, generator=g, dtype=torch.float32) * std).to(p.dtype))
+        else:
+            p.normal_(0.0, std)
+        return
+    key = (p.dtype, float(std))
+    if key not in _TILES:       # one tile per (dtype, std) for the whole model: drawing 4 M values per parameter adds up too
+        _TILES[key] = (torch.randn(_TILE, generator=torch.Generator().manual_seed(12345), dtype=torch.float32) * std).to(p.dtype)
+    tile = _TILES[key]
+    flat = p.view(-1)
+    n = flat.numel()
+    full = n // _TILE
+    if full:
+        flat[:full * _TILE].view(full, _TILE).copy_(tile.unsqueeze(0).expand(full, _TILE))
+    if n - full * _TILE:
+        flat[full * _TILE:].copy_(tile[:n - full * _TILE])
+
+
 def _randomize(module, seed: int, std: float = 0.02):
     g = torch.Generator(device="cpu").manual_seed(seed)
     with torch.no_grad():
@@ -72,10 +100,8 @@ def _randomize(module, seed: int, std: float = 0.02):
                 p.fill_(1.0)
             elif p.dim() == 1:
                 p.zero_()
-            elif p.device.type == "cpu":
-                p.copy_((torch.randn(p.shape, generator=g, dtype=torch.float32) * std).to(p.dtype))
             else:
-                p.normal_(0.0, std)
+                _fill_normal(p, std, g)
 
 
 def build_pipeline(model: str = "BitDance-14B-64x", device: str = "cpu", seed: int = 0, with_ae: bool = True):
@@ -99,7 +125,7 @@ def build_pipeline(model: str = "BitDance-14B-64x", device: str = "cpu", seed: i
             if p.dim() == 1:
                 p.fill_(1.0)
             else:
-                p.normal_(0.0, 0.02)
+                _fill_normal(p, 0.02)
     with torch.device(device):
         head = ref.fh.DiffHead(parallel_num=m["parallel_num"], **m["head"]).eval()
         proj = ref.mu.MLPconnector(m["ae"]["z_channels"], lc["hidden_size"], "gelu_pytorch_tanh").eval()
