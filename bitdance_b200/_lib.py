@@ -83,3 +83,14 @@ def require_cuda(*tensors: torch.Tensor) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise BitDanceNativeError("bitdance_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+_NOTED = set()
+
+
+def note(msg: str):
+    """One log line per distinct reason when a call leaves a persistent single-kernel path (never silently)."""
+    if msg not in _NOTED:
+        _NOTED.add(msg)
+        import logging
+        logging.getLogger("bitdance_b200").warning(msg)

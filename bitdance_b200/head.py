@@ -11,9 +11,10 @@ import ctypes as C
 import torch
 
 from . import _lib, ops
-from ._lib import check, ptr, stream_ptr
+from ._lib import check, note, ptr, stream_ptr
 
 MAX_BLOCKS = 16
+
 
 
 class HeadBlock(C.Structure):
@@ -117,7 +118,11 @@ class HeadRunner:
         dev = self.device
         D, hidden = ch_latent, self.hidden
         # the persistent kernel needs 16-row units everywhere and one 64-column k-block for the latent bits
-        stream = bool(stream) and D % 64 == 0 and ch_target <= 64 and hidden % 8 == 0 and ch_cond % 8 == 0 and D <= 6144
+        fits = D % 64 == 0 and ch_target <= 64 and hidden % 8 == 0 and ch_cond % 8 == 0 and D <= 6144
+        if stream and not fits:
+            note(f"head dims outside the persistent engine's limits (ch_latent={D}: multiple of 64 and <= 6144; "
+                  f"ch_target={ch_target} <= 64): DiffHead.sample runs on the multi-kernel path")
+        stream = bool(stream) and fits
         assert stream or tiled
         self.w = self._build(state_dict, prefix, "tiled", ch_target, ch_cond, depth_latent, depth_adanln, use_swiglu,
                              head_dim, out_sigmoid) if tiled else None
@@ -205,6 +210,9 @@ class HeadRunner:
             assert self.w is not None
             return self.w
         ok = self.w_stream is not None and rows <= 128 and S + 1 <= 104
+        if self.w_stream is not None and not ok and path is None:
+            note(f"DiffHead.sample with {rows} rows / {S} sampling steps is outside the persistent engine's limits (one "
+                  f"128-row tile, <= 103 steps): multi-kernel path")
         if path == "stream":
             assert ok, "persistent path unavailable for this shape"
         if ok:

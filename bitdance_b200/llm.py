@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib, ops
-from ._lib import check, ptr, stream_ptr
+from ._lib import check, note, ptr, stream_ptr
 
 PAGE = 64
 
@@ -91,7 +91,11 @@ class LlmRunner:
         qkv_n = (Hq + 2 * Hkv) * hd
         if stream is None:  # default: off until opted in (BD_LLM_STREAM=1) — see DESIGN.md section 7
             stream = os.environ.get("BD_LLM_STREAM", "0") == "1"
-        stream = bool(stream) and D % 64 == 0 and I % 64 == 0 and qkv_n % 16 == 0 and D <= 6144
+        fits = D % 64 == 0 and I % 64 == 0 and qkv_n % 16 == 0 and D <= 6144
+        if stream and not fits:
+            note(f"decoder dims outside the persistent engine's limits (hidden={D}: multiple of 64 and <= 6144; MLP={I}: "
+                 f"multiple of 64): AR blocks run as chained kernels")
+        stream = bool(stream) and fits
         n_ctas = ops.stream_num_ctas() if stream else 0
         self._keep = []
         layers = (LlmLayer * L)()
