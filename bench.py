@@ -91,7 +91,7 @@ AR_STEPS_PER_IMAGE = {"BitDance-14B-64x": 64, "BitDance-14B-16x": 256}
 
 
 def reference_sample(model: str, device: str, n_warm: int, n_timed: int, S: int, guidance: float, height: int, bs: int,
-                     threads: int | None = None, with_decode: bool = True, budget_s: float | None = None):
+                     threads: int | None = None, with_decode: bool = True):
     """Times the reference's own ``BitDanceT2IPipeline.gen_image`` (oracle/ref_runner.py: its classes, its loop, random-init
     weights of the named architecture, bf16 autocast as in ``generate()``) on a BOUNDED sample: the causal prefill of the
     cond + uncond prompts, then ``n_warm + n_timed`` AR steps of the unmodified loop (each = 51-evaluation DiffHead.sample
@@ -106,18 +106,6 @@ def reference_sample(model: str, device: str, n_warm: int, n_timed: int, S: int,
         torch.set_num_threads(threads)
     pipe, info = rr.build_pipeline(model, device, with_ae=with_decode)
     note = ""
-    if budget_s is not None and n_warm + n_timed > 2:
-        # keep the whole arm within a few minutes whatever --steps / --warmup the caller passes and however slow the host is:
-        # one calibration call of the unmodified loop (1 AR step, cold: first touch of 33 GB of weights, autocast casts)
-        # sizes the sample; it counts as warm-up
-        cal = rr.run_bounded(pipe, info, n_ar=1, image_px=height, guidance=guidance, S=S, num_images=bs)
-        fit = max(2, int(budget_s / max(cal["ar_s"][0] + 1e-9, 1e-3)))
-        if fit < n_warm + n_timed:
-            new_timed = max(1, min(n_timed, fit - 1))
-            new_warm = max(1, min(n_warm, fit - new_timed))
-            note = (f" [bounded: calibration step {cal['ar_s'][0]:.2f} s, {budget_s:.0f} s budget -> {new_warm} warm-up + "
-                    f"{new_timed} timed steps instead of {n_warm} + {n_timed}]")
-            n_warm, n_timed = new_warm, new_timed
     run = rr.run_bounded(pipe, info, n_ar=n_warm + n_timed, image_px=height, guidance=guidance, S=S, num_images=bs)
     timed = run["ar_s"][n_warm:]
     ar = statistics.median(timed)
@@ -134,22 +122,140 @@ def reference_sample(model: str, device: str, n_warm: int, n_timed: int, S: int,
     return out
 
 
+class CpuReferenceWorker:
+    """The unmodified ``gen_image`` on the HOST cores in a subprocess (``python -m oracle.ref_runner``) that logs every event
+    as it happens and is killed at its deadline. ``hold=True``: the worker imports and builds the 33 GB model with 4 threads
+    right away (overlapping whatever the caller does meanwhile) and waits for ``release()`` before it computes."""
+
+    def __init__(self, model: str, n_warm: int, n_timed: int, S: int, guidance: float, height: int, bs: int,
+                 with_decode: bool = False, hold: bool = False):
+        import subprocess
+        import tempfile
+        from oracle import ref_runner as rr
+        self.args = dict(model=model, n_warm=n_warm, S=S, bs=bs)
+        self.threads = rr.usable_cpus()
+        prog = tempfile.NamedTemporaryFile(prefix="bd_ref_progress_", suffix=".jsonl", delete=False)
+        prog.close()
+        self.progress = prog.name
+        self.go_file = prog.name + ".go" if hold else ""
+        cmd = [sys.executable, "-m", "oracle.ref_runner", "--model", model, "--device", "cpu", "--n-ar", str(n_warm + n_timed),
+               "--S", str(S), "--guidance", str(guidance), "--px", str(height), "--bs", str(bs), "--threads", str(self.threads),
+               "--decode", "1" if with_decode else "0", "--progress", self.progress] + (["--go-file", self.go_file] if hold else [])
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")   # host-only: flash_attn etc. see the CPU-only process they are tested in
+        self.t0 = time.perf_counter()
+        self.proc = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+
+    def release(self):
+        if self.go_file:
+            open(self.go_file, "w").close()
+
+    def result(self, deadline_s: float):
+        """Wait at most ``deadline_s`` (from now), kill, derive the number from the event log."""
+        import subprocess
+        killed = False
+        try:
+            err = self.proc.communicate(timeout=deadline_s)[1]
+        except subprocess.TimeoutExpired:
+            self.proc.kill()                              # exactly the process we started
+            err = self.proc.communicate()[1]
+            killed = True
+        wall = time.perf_counter() - self.t0
+        ev = []
+        with open(self.progress) as f:
+            for ln in f:
+                try:
+                    ev.append(json.loads(ln))
+                except ValueError:
+                    pass
+        for path in (self.progress, self.go_file):
+            if path and os.path.exists(path):
+                os.unlink(path)
+        if not killed and self.proc.returncode != 0:
+            raise RuntimeError(f"reference worker failed: {(err or b'').decode(errors='replace')[-300:]}")
+        return derive_reference_sample(ev, killed=killed, wall=wall, threads=self.threads, deadline_s=deadline_s, **self.args)
+
+    def abort(self):
+        if self.proc.poll() is None:
+            self.proc.kill()
+            self.proc.communicate()
+        for path in (self.progress, self.go_file):
+            if path and os.path.exists(path):
+                os.unlink(path)
+
+
+def cpu_reference_sample(model: str, n_warm: int, n_timed: int, S: int, guidance: float, height: int, bs: int,
+                         deadline_s: float, with_decode: bool = False):
+    """One AR step of the 14B reference costs seconds on some hosts and many minutes on others, so the number is derived
+    from whatever finished before the deadline — in this order of preference:
+      (a) complete AR steps (median of those after the warm-up ones);
+      (b) fewer complete steps than asked: the median of the complete ones (the first excluded when there are several);
+      (c) no complete step: per-call stopwatches around the reference's own ``TransEncoder.forward`` and ``Qwen3Model.forward``
+          INSIDE the running loop -> AR step = (S + 1) x median evaluation + 2 x median block pass (labelled).
+    Raises RuntimeError when not even (c) is possible. Returns the same dict as reference_sample."""
+    return CpuReferenceWorker(model, n_warm, n_timed, S, guidance, height, bs, with_decode).result(deadline_s)
+
+
+def derive_reference_sample(ev, *, killed: bool, wall: float, threads: int, model: str, n_warm: int, S: int, bs: int,
+                            deadline_s: float):
+    """The number from the worker's event log (see cpu_reference_sample). Pure: tests/test_bench_reference_arm_cpu.py."""
+    import statistics
+    built = next((e["s"] for e in ev if e["ev"] == "built"), None)
+    if built is None:
+        raise RuntimeError(f"the reference model was not built within {deadline_s:.0f} s on {threads} host threads")
+    steps_t = [e["t"] for e in ev if e["ev"] == "step"]
+    gen0 = next((e["t"] for e in ev if e["ev"] == "gen_start"), None)
+    done = next((e for e in ev if e["ev"] == "gen_done"), None)
+    evals = [e for e in ev if e["ev"] == "eval"]
+    llm = [e for e in ev if e["ev"] == "llm"]
+    pn = next((e.get("pn") for e in ev if e["ev"] == "built"), None) or 64
+    if done is not None:
+        ar_all = done["ar_s"]
+    else:
+        ar_all = [steps_t[i + 1] - steps_t[i] for i in range(len(steps_t) - 1)]   # complete steps only
+    # prefill = everything gen_image does before the first head evaluation (4 Qwen3 passes + embeddings)
+    first_eval_t0 = (evals[0]["t"] - evals[0]["s"]) if evals else None
+    prefill = (first_eval_t0 - gen0) if (first_eval_t0 is not None and gen0 is not None) else None
+    if len(ar_all) > n_warm:
+        ar, how = statistics.median(ar_all[n_warm:]), f"{n_warm} warm-up + {len(ar_all) - n_warm} timed AR steps"
+    elif ar_all:
+        use = ar_all[1:] if len(ar_all) > 1 else ar_all
+        ar, how = statistics.median(use), f"{len(ar_all)} complete AR step(s) before the deadline (median of {len(use)})"
+    else:
+        # a block pass = a Qwen3Model call over parallel_num rows per sequence (the two first-block passes of the prefill
+        # have the same shape as the two passes of an AR step, over a shorter cache)
+        blk = [e["s"] for e in llm if e["rows"] == pn * bs]
+        ev_use = [e["s"] for e in (evals[1:] if len(evals) > 2 else evals)]
+        if not ev_use or not blk:
+            raise RuntimeError(f"not one head evaluation + one block pass of the reference finished within {deadline_s:.0f} s on "
+                               f"{threads} host threads (build {built:.0f} s, {len(llm)} Qwen3 passes, {len(evals)} evaluations)")
+        ar = (S + 1) * statistics.median(ev_use) + 2 * statistics.median(blk)
+        how = (f"NO complete AR step before the deadline: AR step = {S + 1} x median DiffHead evaluation "
+               f"({statistics.median(ev_use):.2f} s, {len(ev_use)} samples) + 2 x median Qwen3 block pass ({statistics.median(blk):.2f} s, "
+               f"{len(blk)} samples), stopwatches around the reference's own modules inside its running loop")
+    dec = next((e["s"] for e in ev if e["ev"] == "decode"), 0.0)
+    steps = AR_STEPS_PER_IMAGE.get(model, 64)
+    sec = prefill + steps * ar + dec
+    desc = (f"unmodified reference gen_image on cpu ({threads} host threads of {os.cpu_count()}, bf16 autocast, random-init {model}), "
+            f"subprocess {'killed at its ' + format(deadline_s, '.0f') + ' s deadline' if killed else 'finished in ' + format(wall, '.0f') + ' s'}: "
+            f"build {built:.0f} s, prefill {prefill:.2f} s, {how}; AR step {ar:.3f} s; decode "
+            f"{'%.2f s' % dec if dec else 'not timed'}; image = prefill + {steps} x AR step + decode (extrapolated)")
+    return dict(n_warm=min(n_warm, max(0, len(ar_all) - 1)), n_timed=max(0, len(ar_all) - n_warm), images_per_s=bs / sec, ar_step_s=ar,
+                prefill_s=prefill, decode_s=dec, build_s=built, sample=desc, measured_s=wall, threads=threads)
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # this arm is host-only: hide the GPUs before anything initialises CUDA, so that the reference (and the libraries it
-    # imports: flash_attn has no CPU backend) sees the same CPU-only process it is tested in
-    os.environ["CUDA_VISIBLE_DEVICES"] = ""
-    threads = os.cpu_count() or 1
     B, S = args.bs, args.sampling_steps
     try:
-        r = reference_sample(args.model, "cpu", args.warmup, args.steps, S, args.guidance, args.height, B, threads,
-                             budget_s=150.0)
-    except Exception as e:  # the shipped copy is missing (oracle/make_ref.py not run) or the host cannot hold the model
-        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"[:300]}))
+        r = cpu_reference_sample(args.model, args.warmup, args.steps, S, args.guidance, args.height, B,
+                                 deadline_s=float(os.environ.get("BD_REF_DEADLINE_S", "270")), with_decode=True)
+    except Exception as e:  # the shipped copy is missing (oracle/make_ref.py not run) or the host cannot hold / run the model
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"[:400]}))
         return
+    threads = r["threads"]
     value = r["images_per_s"]
     steps = AR_STEPS_PER_IMAGE.get(args.model, 64)
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -190,6 +296,18 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+
+    cpu_worker = None
+    have_ref = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "reference")) or os.path.isdir("/root/reference/modeling")
+    if have_ref and not args.no_cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        # cpu_baseline (rank 0, N = 1): the host-core worker imports and builds its 33 GB model NOW, with 4 threads, while
+        # the GPU arm runs; it computes only after release(), when every GPU measurement is done
+        import atexit
+        try:
+            cpu_worker = CpuReferenceWorker(args.model, 1, 1, args.sampling_steps, args.guidance, args.height, args.bs, hold=True)
+            atexit.register(cpu_worker.abort)
+        except Exception:
+            cpu_worker = None
 
     import torch
     import torch.distributed as dist
@@ -387,11 +505,13 @@ def main():
             torch.cuda.empty_cache()
         except Exception as e:
             line["gpu_eager_reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
-            threads = os.cpu_count() or 1
-            r = reference_sample(args.model, "cpu", 1, 1, S, args.guidance, args.height, B, threads, with_decode=False)
-            line["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": threads, "kind": "reference",
+            if cpu_worker is None:
+                raise RuntimeError("the reference is not shipped (oracle/make_ref.py) or the worker could not start")
+            cpu_worker.release()
+            r = cpu_worker.result(float(os.environ.get("BD_CPU_BASELINE_DEADLINE_S", "150")))
+            line["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": r["threads"], "kind": "reference",
                                     "sample": r["sample"] + " [decode not timed in this leg]"}
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "reference",

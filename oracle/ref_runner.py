@@ -126,10 +126,16 @@ def build_pipeline(model: str = "BitDance-14B-64x", device: str = "cpu", seed: i
                 p.fill_(1.0)
             else:
                 _fill_normal(p, 0.02)
-    with torch.device(device):
+    # on the host the constructors' own (serial) initialisers cost ~1 min for the 1.76 B-parameter head: build on the meta
+    # device and materialise empty — _randomize below writes EVERY parameter, and these modules have no buffers
+    with torch.device("meta" if device == "cpu" else device):
         head = ref.fh.DiffHead(parallel_num=m["parallel_num"], **m["head"]).eval()
         proj = ref.mu.MLPconnector(m["ae"]["z_channels"], lc["hidden_size"], "gelu_pytorch_tanh").eval()
         ae = ref.ae.VQModel(m["ae"]).eval() if with_ae else None
+    if device == "cpu":
+        assert not list(head.buffers()) and not list(proj.buffers()) and (ae is None or not list(ae.buffers()))
+        head, proj = head.to_empty(device=device), proj.to_empty(device=device)
+        ae = ae.to_empty(device=device) if ae is not None else None
     _randomize(head, seed + 2)   # incl. the tensors the reference zero-initialises
     _randomize(proj, seed + 4)
     if ae is not None:
@@ -216,3 +222,112 @@ def time_decode(pipe, *, image_px: int = 1024, num_images: int = 1, reps: int = 
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     return best
+
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Time-bounded worker (bench.py's host-core arms). One AR step of the 14B reference is ~26 TFLOP of bf16 GEMM on the host:
+# seconds on an AMX box, many minutes on others (round 2 measured both), so the CPU arm runs in a SUBPROCESS that logs every
+# event as it happens — built, every Qwen3Model pass, every DiffHead network evaluation, every AR step — and the parent
+# kills it at its deadline and derives the number from whatever finished (bench.py::cpu_reference_sample).
+# ---------------------------------------------------------------------------------------------------------------------
+def usable_cpus() -> int:
+    """Host threads this process may really use: cpu_count, limited by the affinity mask and the cgroup CPU quota (an
+    OpenMP team wider than the quota spins on its barriers and runs orders of magnitude slower)."""
+    import math
+    import os
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, math.floor(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
+def _worker(argv=None):
+    import argparse
+    import json
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="BitDance-14B-64x")
+    ap.add_argument("--device", default="cpu")
+    ap.add_argument("--n-ar", type=int, default=2)
+    ap.add_argument("--S", type=int, default=50)
+    ap.add_argument("--guidance", type=float, default=7.5)
+    ap.add_argument("--px", type=int, default=1024)
+    ap.add_argument("--bs", type=int, default=1)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--decode", type=int, default=0)
+    ap.add_argument("--progress", required=True)
+    ap.add_argument("--go-file", default="", help="build with a few threads, then wait for this file before computing "
+                                                  "(bench.py overlaps import + build with its GPU arm, not the compute)")
+    a = ap.parse_args(argv)
+    out = open(a.progress, "a", buffering=1)
+
+    def emit(**kw):
+        kw["t"] = time.perf_counter()
+        out.write(json.dumps(kw) + "\n")
+        out.flush()
+
+    threads = a.threads or usable_cpus()
+    import os
+    if a.device == "cpu":
+        torch.set_num_threads(min(threads, 4) if a.go_file else threads)
+    emit(ev="start", threads=threads, cpu_count=os.cpu_count())
+    pipe, info = build_pipeline(a.model, a.device, with_ae=bool(a.decode))
+    emit(ev="built", s=info["build_s"], pn=pipe.parallel_num)
+    if a.go_file:
+        parent, t_wait = os.getppid(), time.perf_counter()
+        while not os.path.exists(a.go_file):
+            if os.getppid() != parent or time.perf_counter() - t_wait > 1800:   # the bench died / forgot us: do not linger
+                emit(ev="abandoned")
+                return
+            time.sleep(0.2)
+        if a.device == "cpu":
+            torch.set_num_threads(threads)
+        emit(ev="go")
+
+    def timed(name, fn, rows_of):
+        def wrapper(*args, **kw):
+            t0 = time.perf_counter()
+            r = fn(*args, **kw)
+            emit(ev=name, s=time.perf_counter() - t0, rows=rows_of(args, kw))
+            return r
+        return wrapper
+
+    # harness-side stopwatches around two of the reference's own modules (nothing inside them is touched)
+    net = pipe.vision_head.net
+    net.forward = timed("eval", net.forward, lambda args, kw: int(args[0].shape[0] * args[0].shape[1]) if args else 0)
+    lm = pipe.llm_model.model
+    lm.forward = timed("llm", lm.forward, lambda args, kw: int(kw["inputs_embeds"].shape[0] * kw["inputs_embeds"].shape[1])
+                       if "inputs_embeds" in kw else 0)
+
+    base_update = _StepClock.update
+
+    def update(self, n=1):
+        base_update(self, n)
+        emit(ev="step")
+
+    _StepClock.update = update          # this process exists only for this run
+    emit(ev="gen_start")
+    run = run_bounded(pipe, info, n_ar=a.n_ar, image_px=a.px, guidance=a.guidance, S=a.S, num_images=a.bs)
+    emit(ev="gen_done", prefill_s=run["prefill_s"], ar_s=run["ar_s"], total_s=run["total_s"])
+    if a.decode:
+        emit(ev="decode", s=time_decode(pipe, image_px=a.px, num_images=a.bs))
+    emit(ev="done")
+
+
+if __name__ == "__main__":
+    _worker()

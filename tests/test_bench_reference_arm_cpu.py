@@ -1,6 +1,7 @@
 """``bench.py --impl reference`` (the driver's reference arm) on the "tiny" configuration: runs the UNMODIFIED reference's
 ``gen_image`` on the host cores, prints ONE JSON line with the contract keys, and bounds its sample (calibration step +
-time budget) whatever --steps / --warmup are passed. Needs the reference (dev container, or oracle/_ref on the GPU box)."""
+deadline: the host arm runs in a killable subprocess and the number is derived from whatever finished) whatever
+--steps / --warmup are passed. Needs the reference (dev container, or oracle/_ref on the GPU box)."""
 import json
 import os
 import subprocess
@@ -33,25 +34,53 @@ def test_reference_arm_line():
     assert line["config"]["ar_steps_run"] == {"warmup": 1, "timed": 2}
 
 
-def test_reference_sample_is_bounded(monkeypatch):
-    """a slow host (calibration step >> budget) shrinks the sample to 1 warm-up + 1 timed step and says so"""
+def test_reference_arm_deadline_is_reported_not_fatal():
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", BD_REF_DEADLINE_S="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "tiny"],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    line = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][0])
+    assert p.returncode == 0 and line["impl"] == "reference" and "not built within 1 s" in line["unavailable"]
+
+
+def _log(n_steps_done, n_evals_extra=0, done=False, S=3):
+    """a worker event log: build, gen_start, 4 prefill passes, then per AR step S+1 evaluations + 2 block passes"""
+    ev, t = [dict(ev="start", t=0.0, threads=4), dict(ev="built", t=5.0, s=5.0, pn=16), dict(ev="gen_start", t=5.0)], 5.0
+    for rows in (66, 16, 5, 16):
+        t += 2.0
+        ev.append(dict(ev="llm", t=t, s=2.0, rows=rows))
+    for k in range(n_steps_done + 1):
+        ev.append(dict(ev="step", t=t))
+        n_ev = (S + 1) if k < n_steps_done else n_evals_extra
+        for _ in range(n_ev):
+            t += 1.0
+            ev.append(dict(ev="eval", t=t, s=1.0, rows=32))
+        if k < n_steps_done:
+            for _ in range(2):
+                t += 3.0
+                ev.append(dict(ev="llm", t=t, s=3.0, rows=16))
+    if done:
+        ev = [e for e in ev[:-1]] if ev[-1]["ev"] == "step" else ev
+        ev.append(dict(ev="gen_done", t=t, prefill_s=8.0, ar_s=[10.0] * n_steps_done, total_s=t - 5.0))
+    return ev
+
+
+def test_derive_reference_sample_from_partial_logs():
     sys.path.insert(0, ROOT)
     import bench
-    from oracle import ref_runner as rr
-    calls = []
-    real = rr.run_bounded
-
-    def slow(pipe, info, *, n_ar, **kw):
-        calls.append(n_ar)
-        out = real(pipe, info, n_ar=n_ar, **kw)
-        if len(calls) == 1:
-            out["ar_s"] = [1000.0]          # pretend the cold calibration step took 1000 s
-        return out
-
-    monkeypatch.setattr(rr, "run_bounded", slow)
-    r = bench.reference_sample("tiny", "cpu", 3, 5, 3, 3.0, 256, 1, threads=2, with_decode=False, budget_s=150.0)
-    assert calls == [1, 2] and (r["n_warm"], r["n_timed"]) == (1, 1) and "bounded" in r["sample"]
-    calls.clear()
-    monkeypatch.setattr(rr, "run_bounded", lambda pipe, info, *, n_ar, **kw: (calls.append(n_ar), real(pipe, info, n_ar=n_ar, **kw))[1])
-    r = bench.reference_sample("tiny", "cpu", 3, 5, 3, 3.0, 256, 1, threads=2, with_decode=False, budget_s=150.0)
-    assert calls == [1, 8] and (r["n_warm"], r["n_timed"]) == (3, 5) and "bounded" not in r["sample"]
+    kw = dict(wall=60.0, threads=4, model="tiny", n_warm=1, S=3, bs=1, deadline_s=60.0)
+    # (a) finished: 1 warm-up + 2 timed steps of 10 s; prefill 8 s -> image = 8 + 64 * 10
+    r = bench.derive_reference_sample(_log(3, done=True), killed=False, **kw)
+    assert r["ar_step_s"] == 10.0 and abs(r["prefill_s"] - 8.0) < 1e-9 and abs(1 / r["images_per_s"] - 648.0) < 1e-6
+    assert (r["n_warm"], r["n_timed"]) == (1, 2) and "1 warm-up + 2 timed" in r["sample"]
+    # (b) killed during the 2nd step: one complete step (4 evaluations + 2 block passes = 10 s)
+    r = bench.derive_reference_sample(_log(1, n_evals_extra=2), killed=True, **kw)
+    assert abs(r["ar_step_s"] - 10.0) < 1e-9 and "1 complete AR step" in r["sample"] and "killed" in r["sample"]
+    # (c) killed inside the first step after 3 evaluations: (S + 1) * 1 s + 2 * 2 s (the prefill's first-block passes)
+    r = bench.derive_reference_sample(_log(0, n_evals_extra=3), killed=True, **kw)
+    assert abs(r["ar_step_s"] - (4 * 1.0 + 2 * 2.0)) < 1e-9 and "NO complete AR step" in r["sample"]
+    assert abs(r["prefill_s"] - 8.0) < 1e-9
+    # nothing usable: killed during the prefill
+    with pytest.raises(RuntimeError):
+        bench.derive_reference_sample(_log(0)[:5], killed=True, **kw)
+    with pytest.raises(RuntimeError):
+        bench.derive_reference_sample(_log(0)[:1], killed=True, **kw)
