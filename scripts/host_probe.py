@@ -29,7 +29,7 @@ def main():
     lin_bf = torch.nn.Linear(5120, 15360, bias=False).to(torch.bfloat16)
     lin_f32 = torch.nn.Linear(5120, 15360, bias=True)
     best = (None, 1e9)
-    for t in [usable, 96, 64, 48, 32, 16, 8]:
+    for t in sorted({usable, 96, 64, 48, 32, 16, 8}, reverse=True):
         if t > usable:
             continue
         torch.set_num_threads(t)
@@ -47,15 +47,38 @@ def main():
         if res[0] < best[1]:
             best = (t, res[0])
     p(f"best team size for the 128-row Linear: {best[0]}")
-    # the reference's own head network
+    teams = sorted({usable, best[0]}, reverse=True)
+    # one Qwen3-14B decoder layer (bf16 weights), 64 rows, through transformers — an AR pass is 40 of these
+    from transformers import Qwen3Config, Qwen3Model
+    cfg = Qwen3Config(max_position_embeddings=8192, **{**rr.QWEN3_14B, "num_hidden_layers": 1})
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        lm = Qwen3Model(cfg).eval()
+    finally:
+        torch.set_default_dtype(old)
+    xe = torch.randn(1, 64, 5120).to(torch.bfloat16)
+    for t in teams:
+        torch.set_num_threads(t)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            times = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                lm(inputs_embeds=xe, use_cache=False)
+                times.append(time.perf_counter() - t0)
+        p(f"threads {t:4d}: one Qwen3-14B layer, 64 rows: {[round(v, 3) for v in times]} s  (x40 = one AR pass)")
+    del lm
+    # the reference's own head network (built on the meta device: its serial initialisers cost a minute)
     ref = rr.rh.import_reference()
     t0 = time.perf_counter()
-    head = ref.fh.DiffHead(parallel_num=64, ch_target=32, ch_cond=5120, ch_latent=5120, depth_latent=6, depth_adanln=2,
-                           use_swiglu=True).eval()
+    with torch.device("meta"):
+        head = ref.fh.DiffHead(parallel_num=64, ch_target=32, ch_cond=5120, ch_latent=5120, depth_latent=6, depth_adanln=2,
+                               use_swiglu=True).eval()
+    head = head.to_empty(device="cpu")
     rr._randomize(head, 2)
     p(f"DiffHead built in {time.perf_counter() - t0:.1f} s")
     xs, ts, cs = torch.randn(2, 64, 32), torch.rand(2), torch.randn(2, 64, 5120)
-    for t in sorted({usable, best[0], 32 if usable >= 32 else usable}, reverse=True):
+    for t in teams:
         torch.set_num_threads(t)
         with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
             times = []
@@ -63,6 +86,8 @@ def main():
                 t0 = time.perf_counter()
                 head.net(xs, ts, cs)
                 times.append(time.perf_counter() - t0)
+                if times[-1] > 20:
+                    break
         p(f"threads {t:4d}: TransEncoder.forward (one head evaluation, 128 rows) {[round(v, 2) for v in times]} s")
 
 
