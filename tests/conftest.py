@@ -17,6 +17,12 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
 
+    try:   # GPU boxes show 128 CPUs but grant a 16-CPU cgroup quota (profiles/r02_host_probe.txt): a wider OpenMP team
+        from oracle.ref_runner import usable_cpus   # makes every CPU oracle call crawl
+        torch.set_num_threads(usable_cpus())
+    except Exception:
+        pass
+
     has_gpu = torch.cuda.is_available()
     has_ref = (os.path.isdir("/root/reference/modeling")
                or os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "reference", "modeling")))
