@@ -171,9 +171,11 @@ class MLLModel:
         whole context again on top of the cache — reproduced literally), the sampler (top-k 1200 / top-p 0.95 on the
         global torch generator) and the image generator (= ``gen_image_block_causal`` on the accumulated context).
 
-        Where the reference cannot be followed: its text branch feeds a 2-D ``(1, hidden)`` tensor back as
-        ``inputs_embeds`` and concatenates 1-D token tensors along dim 1 (mllm.py:857,867) — it raises on the second
-        decoded token / at the end; here the evident intent runs (one ``[1, 1, hidden]`` step per token). The reference
+        Where the reference cannot be followed: its text branch raises — without a cache at mllm.py:798 (it subscripts
+        ``past_key_values`` = None before the first pass), with one (after a generated image) on the second token, because
+        the sampled token's 2-D ``(1, hidden)`` embedding is fed back as ``inputs_embeds`` (:857), and it would concatenate
+        1-D token tensors along dim 1 at the end (:867); tests/test_interleaved_vs_reference.py asserts both failures on
+        the unmodified reference. Here the evident intent runs (one ``[1, 1, hidden]`` step per token). The reference
         ignores its ``do_sample`` / ``temperature`` arguments (hard-coded ``True`` / ``1.0`` at the call site); here they
         are honoured, and their defaults are the reference's constants. Its wasted unconditional LLM pass during TEXT
         decoding (computed, never read) is skipped. Not supported (raises): a generated image when the persistent cache is

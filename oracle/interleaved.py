@@ -6,9 +6,10 @@ causal pass over the accumulated context on top of the persistent KV cache, ``hi
 (:829), ``pred_logits = lm_head(hidden_state)`` (:845-846), ``sample_codebook(..., top_k=1200, top_p=0.95)`` (:852-858,
 modeling/utils.py:95-124), the sampled token's embedding is the next input, stop on ``<|im_end|>`` (:863-866).
 
-Pinning. The reference's own text branch cannot run (it feeds a 2-D ``(1, hidden)`` tensor back as ``inputs_embeds`` and
-concatenates 1-D token tensors along dim 1, :857,867 — it raises), so there is no reference output to pin the LOOP
-against: **the loop is parity-unpinned**. What is pinned: the decoder (``oracle/llm.py``, against transformers' Qwen3Model,
+Pinning. The reference's own text branch cannot run: without a cache it subscripts ``past_key_values = None`` (:798), after
+a generated image it feeds the sampled token's 2-D ``(1, hidden)`` embedding back as ``inputs_embeds`` (:857) and the decoder
+fails on the second token (tests/test_interleaved_vs_reference.py asserts both on the unmodified reference). So there is no
+reference output to pin the LOOP against: **the loop is parity-unpinned**. What is pinned: the decoder (``oracle/llm.py``, against transformers' Qwen3Model,
 tests/test_oracle_vs_reference.py), and the sampler — ``tests/test_interleaved_cpu.py`` checks the mirrored
 ``top_k_top_p_filtering`` / ``sample_codebook`` / ``remove_first_user_block`` bit-exactly against the unmodified reference
 functions; this file calls the mirrored sampler through the ``sampler`` argument or plain argmax.

@@ -38,18 +38,26 @@ def projector(sd, x, rnd):
 
 
 def gen_image(*, sd_llm, cfg_llm, embed, sd_head, sd_proj, sd_ae, cond_ids, uncond_ids, start_ids, h, w, pn,
-              num_images, guidance, S, noise, rnd=ident, head_dim=128, decode=True, trace=None, num_steps=None):
+              num_images, guidance, S, noise, rnd=ident, head_dim=128, decode=True, trace=None, num_steps=None,
+              cond_emb=None, uncond_emb=None):
     """noise: list over AR steps of lists [x0, eps_0 .. eps_{S-1}] (the torch.randn sequence of one sample() call).
     embed: [vocab, hidden] embedding table. start_ids: pn + 2 token ids (<|vision_start|>, <|res_h|>, <|res_w|>,
-    <|query_1..pn-1|>). Returns (tokens [B, h*w, C], image | None)."""
+    <|query_1..pn-1|>). ``cond_emb`` / ``uncond_emb`` [L, hidden]: context EMBEDDINGS instead of ``embed[cond_ids]`` — the
+    interleaved inference's image item (modeling/mllm.py:745-783), whose context also holds projected image tokens.
+    Returns (tokens [B, h*w, C], image | None)."""
     B, L = num_images, cfg_llm["num_hidden_layers"]
     hidden_size = embed.shape[1]
     ps = int(pn ** 0.5)
     pos = pos_embed_2d(hidden_size, h, w, ps)
     groups = [cond_ids] + ([uncond_ids] if guidance > 1.0 else [])
+    ctx_emb = [cond_emb] + ([uncond_emb] if guidance > 1.0 else [])
     caches, hid = [], []
-    for ids in groups:
-        emb = rnd(embed[torch.tensor(list(ids) + list(start_ids))].float()).unsqueeze(0).repeat(B, 1, 1)
+    for ids, ce in zip(groups, ctx_emb):
+        if ce is None:
+            emb = embed[torch.tensor(list(ids) + list(start_ids))].float()
+        else:
+            emb = torch.cat([ce.float(), embed[torch.tensor(list(start_ids))].float()], dim=0)
+        emb = rnd(emb).unsqueeze(0).repeat(B, 1, 1)
         cache = [None] * L
         ollm.decoder_forward(sd_llm, cfg_llm, emb[:, :-pn], cache, causal=True, rnd=rnd, stream_f32=(rnd is ident))
         o = ollm.decoder_forward(sd_llm, cfg_llm, emb[:, -pn:], cache, causal=False, rnd=rnd, stream_f32=(rnd is ident))

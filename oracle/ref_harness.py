@@ -113,3 +113,28 @@ def import_reference():
     _done = True
     _ns = types.SimpleNamespace(fh=fh, sx=sx, ae=ae, mu=mu, t2i=t2i)
     return _ns
+
+
+def import_reference_mllm():
+    """The reference's ``modeling/mllm.py`` (dev container only: it imports the reference's ``data`` package, which is not
+    shipped to the GPU box). Used by tests/test_interleaved_cpu.py to pin the interleaved plan bookkeeping against the
+    reference's own ``forward_inference_block_causal`` and to show that its text branch raises."""
+    import_reference()
+    mine = {k: v for k, v in sys.modules.items() if k == "modeling" or k.startswith("modeling.")}
+    for k in mine:
+        del sys.modules[k]
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hidden = [(i, p) for i, p in enumerate(sys.path) if os.path.abspath(p or os.getcwd()) == repo_root]
+    for _, p in hidden:
+        sys.path.remove(p)
+    sys.path.insert(0, REF)
+    try:
+        import modeling.mllm as mllm
+    finally:
+        sys.path.remove(REF)
+        for i, p in hidden:
+            sys.path.insert(min(i, len(sys.path)), p)
+        for k in [k for k in sys.modules if k == "modeling" or k.startswith("modeling.")]:
+            del sys.modules[k]
+        sys.modules.update(mine)
+    return mllm
