@@ -42,6 +42,14 @@ def test_reference_arm_deadline_is_reported_not_fatal():
     assert p.returncode == 0 and line["impl"] == "reference" and "not built within 1 s" in line["unavailable"]
 
 
+def test_reference_arm_other_ranks_do_nothing():
+    """under torchrun (N > 1) rank 0 alone runs the arm; the other ranks exit 0 without work or output"""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--model", "tiny"],
+                       capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
 def _log(n_steps_done, n_evals_extra=0, done=False, S=3):
     """a worker event log: build, gen_start, 4 prefill passes, then per AR step S+1 evaluations + 2 block passes"""
     ev, t = [dict(ev="start", t=0.0, threads=4), dict(ev="built", t=5.0, s=5.0, pn=16), dict(ev="gen_start", t=5.0)], 5.0
