@@ -92,3 +92,28 @@ def test_derive_reference_sample_from_partial_logs():
         bench.derive_reference_sample(_log(0)[:5], killed=True, **kw)
     with pytest.raises(RuntimeError):
         bench.derive_reference_sample(_log(0)[:1], killed=True, **kw)
+
+
+def test_usable_cpus_honours_the_cgroup_quota(tmp_path):
+    """profiles/r02_host_probe.txt: a GPU box shows 128 CPUs and grants ``cpu.max = 1600000 100000`` (16 CPUs)"""
+    sys.path.insert(0, ROOT)
+    from oracle.ref_runner import usable_cpus
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    (tmp_path / "cpu.max").write_text("200000 100000\n")
+    assert usable_cpus(str(tmp_path)) == min(n, 2)
+    (tmp_path / "cpu.max").write_text("max 100000\n")
+    assert usable_cpus(str(tmp_path)) == n
+    (tmp_path / "cpu.max").write_text("50000 100000\n")          # half a CPU still means one thread
+    assert usable_cpus(str(tmp_path)) == 1
+    (tmp_path / "cpu.max").unlink()
+    (tmp_path / "cpu").mkdir()
+    (tmp_path / "cpu" / "cpu.cfs_quota_us").write_text("300000\n")     # cgroup v1
+    (tmp_path / "cpu" / "cpu.cfs_period_us").write_text("100000\n")
+    assert usable_cpus(str(tmp_path)) == min(n, 3)
+    (tmp_path / "cpu" / "cpu.cfs_quota_us").write_text("-1\n")
+    assert usable_cpus(str(tmp_path)) == n
+    assert usable_cpus(str(tmp_path / "missing")) == n
