@@ -312,6 +312,11 @@ def main():
     import torch
     import torch.distributed as dist
 
+    try:   # host-side torch ops of this process: never a wider OpenMP team than the cgroup grants (16 of 128 on this pool)
+        from oracle.ref_runner import usable_cpus
+        torch.set_num_threads(max(1, min(torch.get_num_threads(), usable_cpus())))
+    except Exception:
+        pass
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
