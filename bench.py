@@ -313,7 +313,7 @@ def main():
     import torch.distributed as dist
 
     try:   # host-side torch ops of this process: never a wider OpenMP team than the cgroup grants (16 of 128 on this pool)
-        from oracle.ref_runner import usable_cpus
+        from bitdance_b200.hostinfo import usable_cpus
         torch.set_num_threads(max(1, min(torch.get_num_threads(), usable_cpus())))
     except Exception:
         pass

@@ -18,7 +18,7 @@ def pytest_collection_modifyitems(config, items):
     import torch
 
     try:   # GPU boxes show 128 CPUs but grant a 16-CPU cgroup quota (profiles/r02_host_probe.txt): a wider OpenMP team
-        from oracle.ref_runner import usable_cpus   # makes every CPU oracle call crawl
+        from bitdance_b200.hostinfo import usable_cpus   # makes every CPU oracle call crawl
         torch.set_num_threads(usable_cpus())
     except Exception:
         pass

@@ -97,7 +97,7 @@ def test_derive_reference_sample_from_partial_logs():
 def test_usable_cpus_honours_the_cgroup_quota(tmp_path):
     """profiles/r02_host_probe.txt: a GPU box shows 128 CPUs and grants ``cpu.max = 1600000 100000`` (16 CPUs)"""
     sys.path.insert(0, ROOT)
-    from oracle.ref_runner import usable_cpus
+    from bitdance_b200.hostinfo import usable_cpus
     n = os.cpu_count() or 1
     try:
         n = min(n, len(os.sched_getaffinity(0)))
