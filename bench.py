@@ -131,9 +131,9 @@ class CpuReferenceWorker:
                  with_decode: bool = False, hold: bool = False):
         import subprocess
         import tempfile
-        from oracle import ref_runner as rr
+        from bitdance_b200.hostinfo import usable_cpus
         self.args = dict(model=model, n_warm=n_warm, S=S, bs=bs)
-        self.threads = rr.usable_cpus()
+        self.threads = usable_cpus()
         prog = tempfile.NamedTemporaryFile(prefix="bd_ref_progress_", suffix=".jsonl", delete=False)
         prog.close()
         self.progress = prog.name
