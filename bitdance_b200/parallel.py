@@ -47,8 +47,16 @@ def gather_token_grids(packed_local: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
-def broadcast_tensors(tensors, src: int = 0, group=None) -> None:
+def broadcast_tensors(tensors, src: int = 0, group=None, include_integer: bool = False) -> int:
+    """Start-up broadcast of prepacked WEIGHTS from ``src``. Integer tensors are skipped unless asked for: the engines keep
+    tables of DEVICE POINTERS (int64 addresses of the local process's allocations, e.g. the per-layer table of the
+    one-launch Qwen3 block) next to their weights, and another rank's addresses are poison. Returns the bytes shipped."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return
+        return 0
+    n = 0
     for t in tensors:
+        if t is None or (not include_integer and not (t.is_floating_point() or t.is_complex())):
+            continue
         dist.broadcast(t, src=src, group=group)
+        n += t.numel() * t.element_size()
+    return n

@@ -32,9 +32,12 @@ def _worker(rank, world, port, q):
     try:
         local = (torch.arange(2 * 6 * 1, dtype=torch.int32).view(2, 6, 1) + 1000 * rank)
         out = par.gather_token_grids(local)
-        w = [torch.full((3,), float(rank))]
-        par.broadcast_tensors(w, src=0)
-        q.put((rank, out.tolist(), w[0].tolist()))  # plain lists: no fd-passing of tensor storages after exit
+        # a weight set as the engines keep it: float payload + a table of process-local device pointers (int64)
+        w = [torch.full((3,), float(rank)), torch.full((2,), 7000 + rank, dtype=torch.int64), None,
+             torch.full((4,), float(rank)).to(torch.bfloat16)]
+        shipped = par.broadcast_tensors(w, src=0)
+        assert shipped == 3 * 4 + 4 * 2
+        q.put((rank, out.tolist(), w[0].tolist(), w[1].tolist(), w[3].float().tolist()))  # plain lists: no fd-passing
     finally:
         dist.destroy_process_group()
 
@@ -52,6 +55,7 @@ def test_gather_token_grids_gloo_world2():
         assert p.exitcode == 0
     base = torch.arange(12, dtype=torch.int32).view(2, 6, 1)
     want = torch.cat([base, base + 1000], dim=0)
-    for rank, out, w in res:
+    for rank, out, w, table, wb in res:
         assert out == want.tolist()   # rank-major, identical on every rank
-        assert w == [0.0, 0.0, 0.0]  # broadcast from rank 0
+        assert w == [0.0, 0.0, 0.0] and wb == [0.0] * 4  # broadcast from rank 0
+        assert table == [7000 + rank] * 2               # the pointer table stays the receiver's own
