@@ -207,3 +207,29 @@ def test_forward_dispatch():
     m.training = True
     with pytest.raises(NotImplementedError):
         m.forward()
+
+
+def test_cache_capacity_bound_holds_for_random_chat_plans():
+    """the persistent conditional cache is allocated once, up front (``_interleaved_capacity``): the stub decoder asserts on
+    every appended token that it still fits, over random multi-turn plans incl. cut-off turns (context re-fed literally)"""
+    import random
+    rnd = random.Random(0)
+    for trial in range(40):
+        n_turns = rnd.randint(1, 5)
+        max_len = rnd.randint(1, 6)
+        plan, texts, script = [], [], []
+        for _ in range(n_turns):
+            for _ in range(rnd.randint(1, 2)):                  # one or two user items before every model turn
+                if rnd.random() < 0.3:
+                    plan.append(dict(type="image", **{"from": "user"}))
+                else:
+                    plan.append(dict(type="text", **{"from": "user"}))
+                    texts.append("x" * rnd.randint(1, 9))
+            plan.append(dict(type="text", **{"from": "model"}))
+            ends_at = rnd.randint(1, max_len + 2)               # beyond max_len: the turn is cut off
+            script += [IM_END if i + 1 == ends_at else 1 + i for i in range(min(max_len, ends_at))]
+        imgs = [torch.zeros(1, 3, 4 * rnd.randint(1, 3), 4 * rnd.randint(1, 3)) for _ in plan if _["type"] == "image"]
+        m, emb, llm, gen = make_stub(script)
+        out = m.forward_inference_block_causal(plan, texts, imgs, max_length_text=max_len, image_size=[8, 8], cfg_scale=1.0,
+                                               do_sample=False)
+        assert len(out["generated_text"]) == n_turns and texts == [] and imgs == []
