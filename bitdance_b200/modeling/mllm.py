@@ -23,8 +23,6 @@ needed: build with ``MLLModel.from_pipeline(pipe)`` or ``MLLModel.from_component
 with the fields the mirrored methods read (``vit_patch_size``, ``encoder.vt_forward_func`` / ``max_bs``)."""
 from __future__ import annotations
 
-import types
-
 import torch
 
 from ..pipeline import pos_embed_2d
